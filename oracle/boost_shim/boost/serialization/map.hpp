@@ -1,0 +1,6 @@
+// Boost shim (oracle build only): serialization/map.hpp
+// Minimal stand-in so the unmodified reference compiles without Boost; see oracle/README.md.
+#ifndef SHIM_SERIALIZATION_MAP_HPP
+#define SHIM_SERIALIZATION_MAP_HPP
+#include <boost/archive/text_oarchive.hpp>
+#endif
