@@ -1,0 +1,923 @@
+// fora_b200/csrc/engine.cu -- C ABI implementation: context, HBM-resident graph, query batching.
+//
+// Host orchestration only; all arithmetic on vectors happens in the kernels of push.cuh /
+// walk.cuh / topk.cuh.  There is no CPU fallback: without a CUDA device fora_ctx_create fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "push.cuh"
+#include "topk.cuh"
+#include "walk.cuh"
+
+using namespace fora;
+
+static std::string g_create_error;
+
+// per-slot metadata, mirrored host <-> device in one copy
+struct SlotMeta {
+    int32_t source[MAX_SLOTS];
+    u32 qid[MAX_SLOTS];
+    double rmax[MAX_SLOTS];
+    int32_t state[MAX_SLOTS];  // 0 unused, 1 active, 2 source without out-edges
+    int32_t active[MAX_SLOTS]; // takes part in the current push round
+    u64 edges[MAX_SLOTS], vertices[MAX_SLOTS], levels[MAX_SLOTS];
+    int32_t lastlvl[MAX_SLOTS];
+    double rsum[MAX_SLOTS];
+    u64 nnz[MAX_SLOTS], nsrc[MAX_SLOTS], nwalk[MAX_SLOTS], hops[MAX_SLOTS], idx_hits[MAX_SLOTS];
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t count) {
+        if (count <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) cap = count;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct fora_ctx {
+    int device = 0;
+    uint64_t seed = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[8] = {};
+    std::string err;
+    int num_sms = 0;
+    DeviceGraph g;
+    fora_params p{};
+    bool params_set = false;
+    int slots = 4;
+    int alloc_slots = 0;
+    // dense per-slot state
+    DevBuf<double> reserve, residue;
+    DevBuf<u64> front0, front1;
+    DevBuf<double> inc;
+    DevBuf<u32> hub;
+    DevBuf<PushCtl> ctl;
+    DevBuf<SlotMeta> meta;
+    SlotMeta* h_meta = nullptr; // pinned
+    DevBuf<double> part_sum;
+    DevBuf<u32> part_nnz;
+    int red_blocks = 0;
+    // plan / walk
+    DevBuf<u32> blk_src;
+    DevBuf<u64> blk_walk;
+    DevBuf<int32_t> srcs;
+    DevBuf<u64> woff;
+    DevBuf<double> incs;
+    DevBuf<u32> chunk_first;
+    size_t chunk_cap = 0;
+    // index
+    DevBuf<u64> idx_off, idx_cnt;
+    DevBuf<int32_t> idx_dest;
+    bool has_index = false;
+    // scratch
+    DevBuf<u64> counts;
+    DevBuf<u64> scratch64;
+    DevBuf<int32_t> scratch32;
+    DevBuf<double> scratchd;
+    int push_grid = 0;
+    u32 level_base = 0;
+    u64 launches = 0;
+    // resumable push session (fora_push_begin / fora_push_round)
+    int32_t session_source = -1;
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return ctx->fail(FORA_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + \
+                                             ":" + std::to_string(__LINE__));                                 \
+    } while (0)
+#define CKL()                                                                                   \
+    do {                                                                                        \
+        ctx->launches++;                                                                        \
+        cudaError_t e__ = cudaGetLastError();                                                   \
+        if (e__ != cudaSuccess)                                                                 \
+            return ctx->fail(FORA_ECUDA, std::string("launch: ") + cudaGetErrorString(e__) + " @" + __FILE__ + \
+                                             ":" + std::to_string(__LINE__));                   \
+    } while (0)
+
+static const double DEFAULT_COST_WALK = 4.0e-10;   // s per online walk   (B200 calibration)
+static const double DEFAULT_COST_EDGE = 5.0e-11;   // s per pushed edge
+static const double DEFAULT_COST_VERTEX = 2.0e-10; // s per pushed vertex
+static const double DEFAULT_COST_LEVEL = 1.0e-6;   // s per frontier level (barrier latency, amortised over slots)
+
+// =============================================================================================
+// context
+// =============================================================================================
+extern "C" int fora_ctx_create(int device, uint64_t seed, fora_ctx** out) {
+    if (!out) return FORA_EINVAL;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)";
+        return FORA_ECUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "bad device ordinal";
+        return FORA_EINVAL;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = cudaGetErrorString(e);
+        return FORA_ECUDA;
+    }
+    fora_ctx* ctx = new fora_ctx();
+    ctx->device = device;
+    ctx->seed = seed;
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->num_sms = prop.multiProcessorCount;
+    if (!prop.cooperativeLaunch) {
+        g_create_error = "device lacks cooperative launch";
+        delete ctx;
+        return FORA_ECUDA;
+    }
+    if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_meta, sizeof(SlotMeta)) != cudaSuccess) {
+        g_create_error = "stream / pinned allocation failed";
+        delete ctx;
+        return FORA_ECUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    memset(ctx->h_meta, 0, sizeof(SlotMeta));
+    ctx->p.alpha = 0.2;
+    *out = ctx;
+    return FORA_OK;
+}
+
+static void free_graph(DeviceGraph& g) {
+    cudaFree(g.out_ptr64); cudaFree(g.out_ptr32); cudaFree(g.out_col); cudaFree(g.deg);
+    cudaFree(g.in_ptr64); cudaFree(g.in_ptr32); cudaFree(g.in_col);
+    g = DeviceGraph();
+}
+
+extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    free_graph(ctx->g);
+    ctx->reserve.release(); ctx->residue.release(); ctx->front0.release(); ctx->front1.release();
+    ctx->inc.release(); ctx->hub.release(); ctx->ctl.release(); ctx->meta.release();
+    ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
+    ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
+    ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
+    ctx->counts.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
+    if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+extern "C" const char* fora_last_error(fora_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int fora_ctx_set_stream(fora_ctx* ctx, void* s) {
+    if (!ctx) return FORA_EINVAL;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return FORA_OK;
+}
+extern "C" int fora_ctx_set_slots(fora_ctx* ctx, int slots) {
+    if (!ctx || slots < 1 || slots > MAX_SLOTS) return ctx ? ctx->fail(FORA_EINVAL, "slots must be in [1,64]") : FORA_EINVAL;
+    ctx->slots = slots;
+    return FORA_OK;
+}
+extern "C" int fora_ctx_sync(fora_ctx* ctx) {
+    if (!ctx) return FORA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+
+// =============================================================================================
+// graph
+// =============================================================================================
+__global__ void degree_kernel(int32_t n, const int64_t* __restrict__ ptr, int32_t* __restrict__ deg, u32* __restrict__ ptr32) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v <= n; v += gridDim.x * blockDim.x) {
+        if (v < n) deg[v] = (int32_t)(ptr[v + 1] - ptr[v]);
+        if (ptr32) ptr32[v] = (u32)ptr[v];
+    }
+}
+
+extern "C" int fora_graph_upload(fora_ctx* ctx, int32_t n, int64_t m_decl, const int64_t* out_ptr, const int32_t* out_col,
+                                 const int64_t* in_ptr, const int32_t* in_col) {
+    if (!ctx) return FORA_EINVAL;
+    if (n <= 0 || !out_ptr || !out_col) return ctx->fail(FORA_EINVAL, "graph_upload: n>0 and out-CSR required");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_graph(ctx->g);
+    DeviceGraph& g = ctx->g;
+    g.n = n;
+    g.m_decl = m_decl;
+    g.n_edges = out_ptr[n];
+    g.off32 = g.n_edges < (int64_t)0xffffffffLL;
+    const size_t ne = (size_t)g.n_edges;
+    CK(cudaMalloc((void**)&g.out_ptr64, sizeof(int64_t) * (size_t)(n + 1)));
+    CK(cudaMalloc((void**)&g.out_col, sizeof(int32_t) * std::max<size_t>(ne, 1)));
+    CK(cudaMalloc((void**)&g.deg, sizeof(int32_t) * (size_t)n));
+    if (g.off32) CK(cudaMalloc((void**)&g.out_ptr32, sizeof(u32) * (size_t)(n + 1)));
+    CK(cudaMemcpyAsync(g.out_ptr64, out_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(g.out_col, out_col, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
+    degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.out_ptr64, g.deg, g.out_ptr32);
+    CKL();
+    if (in_ptr && in_col) {
+        if (in_ptr[n] != g.n_edges) return ctx->fail(FORA_EINVAL, "graph_upload: in-CSR edge count differs from out-CSR");
+        CK(cudaMalloc((void**)&g.in_ptr64, sizeof(int64_t) * (size_t)(n + 1)));
+        CK(cudaMalloc((void**)&g.in_col, sizeof(int32_t) * std::max<size_t>(ne, 1)));
+        if (g.off32) CK(cudaMalloc((void**)&g.in_ptr32, sizeof(u32) * (size_t)(n + 1)));
+        CK(cudaMemcpyAsync(g.in_ptr64, in_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(g.in_col, in_col, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
+        if (g.off32) {
+            DevBuf<int32_t> tmp;
+            CK(tmp.ensure((size_t)n));
+            degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.in_ptr64, tmp.p, g.in_ptr32);
+            CKL();
+            CK(cudaStreamSynchronize(ctx->stream));
+            tmp.release();
+        }
+        g.has_in = true;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->alloc_slots = 0; // dense state is sized by n
+    ctx->has_index = false;
+    ctx->session_source = -1;
+    return FORA_OK;
+}
+
+extern "C" int fora_graph_download_csr(fora_ctx* ctx, int64_t* out_ptr, int32_t* out_col, int64_t* in_ptr, int32_t* in_col) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    const DeviceGraph& g = ctx->g;
+    const size_t ne = (size_t)g.n_edges;
+    if (out_ptr) CK(cudaMemcpyAsync(out_ptr, g.out_ptr64, sizeof(int64_t) * (size_t)(g.n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_col) CK(cudaMemcpyAsync(out_col, g.out_col, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    if (in_ptr || in_col) {
+        if (!g.has_in) return ctx->fail(FORA_EINVAL, "in-CSR was not uploaded");
+        if (in_ptr) CK(cudaMemcpyAsync(in_ptr, g.in_ptr64, sizeof(int64_t) * (size_t)(g.n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+        if (in_col) CK(cudaMemcpyAsync(in_col, g.in_col, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+extern "C" int64_t fora_graph_num_edges(fora_ctx* ctx) { return ctx ? ctx->g.n_edges : FORA_EINVAL; }
+
+// =============================================================================================
+// parameters
+// =============================================================================================
+extern "C" int fora_params_set(fora_ctx* ctx, const fora_params* p) {
+    if (!ctx || !p) return FORA_EINVAL;
+    if (!(p->alpha > 0 && p->alpha < 1)) return ctx->fail(FORA_EINVAL, "alpha must be in (0,1)");
+    ctx->p = *p;
+    if (ctx->p.cost_walk == 0 && ctx->p.cost_edge == 0 && ctx->p.cost_vertex == 0 && ctx->p.cost_level == 0) {
+        ctx->p.cost_walk = DEFAULT_COST_WALK;
+        ctx->p.cost_edge = DEFAULT_COST_EDGE;
+        ctx->p.cost_vertex = DEFAULT_COST_VERTEX;
+        ctx->p.cost_level = DEFAULT_COST_LEVEL;
+    }
+    ctx->params_set = true;
+    return FORA_OK;
+}
+extern "C" int fora_params_get(fora_ctx* ctx, fora_params* p) {
+    if (!ctx || !p) return FORA_EINVAL;
+    *p = ctx->p;
+    return FORA_OK;
+}
+
+// =============================================================================================
+// slot state
+// =============================================================================================
+static int ensure_slots(fora_ctx* ctx, double omega_max) {
+    const DeviceGraph& g = ctx->g;
+    if (!g.n) return ctx->fail(FORA_EINVAL, "no graph uploaded");
+    const int S = ctx->slots;
+    const size_t n = (size_t)g.n;
+    if (ctx->alloc_slots < S) {
+        const size_t fcap = n * S;
+        if (fcap >= 0xffffffffull) return ctx->fail(FORA_EINVAL, "slots*n must stay below 2^32");
+        CK(ctx->reserve.ensure(n * S));
+        CK(ctx->residue.ensure(n * S));
+        CK(ctx->front0.ensure(fcap));
+        CK(ctx->front1.ensure(fcap));
+        CK(ctx->inc.ensure(fcap));
+        CK(ctx->hub.ensure(fcap));
+        CK(ctx->ctl.ensure(1));
+        CK(ctx->meta.ensure(1));
+        ctx->red_blocks = std::max(1, std::min<int>(ctx->num_sms * 4, (int)((n + 4095) / 4096)));
+        CK(ctx->part_sum.ensure((size_t)ctx->red_blocks * S));
+        CK(ctx->part_nnz.ensure((size_t)ctx->red_blocks * S));
+        const size_t nblk = (n + PLAN_THREADS - 1) / PLAN_THREADS;
+        CK(ctx->blk_src.ensure(nblk * S));
+        CK(ctx->blk_walk.ensure(nblk * S));
+        CK(ctx->srcs.ensure(n * S));
+        CK(ctx->woff.ensure((n + 1) * S));
+        CK(ctx->incs.ensure(n * S));
+        ctx->alloc_slots = S;
+        ctx->chunk_cap = 0;
+        // occupancy-sized cooperative grid
+        int per_sm = 0;
+        if (g.off32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<u32>, PUSH_THREADS, 0));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<int64_t>, PUSH_THREADS, 0));
+        if (per_sm < 1) return ctx->fail(FORA_ECUDA, "push kernel does not fit on an SM");
+        ctx->push_grid = per_sm * ctx->num_sms;
+    }
+    // walks per slot <= omega*rsum + #sources <= omega + n
+    const size_t need = (size_t)((omega_max + (double)n) / WALK_CHUNK) + 4;
+    if (need > ctx->chunk_cap || ctx->chunk_first.cap < need * S) {
+        CK(ctx->chunk_first.ensure(need * S));
+        ctx->chunk_cap = need;
+    }
+    return FORA_OK;
+}
+
+static int meta_h2d(fora_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->meta.p, ctx->h_meta, sizeof(SlotMeta), cudaMemcpyHostToDevice, ctx->stream));
+    return FORA_OK;
+}
+static int meta_d2h_sync(fora_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->h_meta, ctx->meta.p, sizeof(SlotMeta), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+
+static PushArgs make_push_args(fora_ctx* ctx) {
+    PushArgs a{};
+    SlotMeta* m = ctx->meta.p;
+    a.n = ctx->g.n;
+    a.slots = ctx->slots;
+    a.alpha = ctx->p.alpha;
+    a.reserve = ctx->reserve.p;
+    a.residue = ctx->residue.p;
+    a.deg = ctx->g.deg;
+    a.front0 = ctx->front0.p;
+    a.front1 = ctx->front1.p;
+    a.inc = ctx->inc.p;
+    a.hub = ctx->hub.p;
+    a.ctl = ctx->ctl.p;
+    a.rmax = m->rmax;
+    a.source = m->source;
+    a.edges = m->edges;
+    a.vertices = m->vertices;
+    a.levels = m->levels;
+    a.lastlvl = m->lastlvl;
+    a.front_cap = (u32)ctx->front0.cap;
+    a.max_levels = 1u << 20;
+    a.level_base = ctx->level_base;
+    return a;
+}
+
+// launch the persistent push kernel over whatever frontier is in front0 / ctl->fcount[0]
+static int launch_push(fora_ctx* ctx) {
+    PushArgs a = make_push_args(ctx);
+    ctx->level_base += (1u << 20);
+    if (ctx->g.off32) {
+        CsrView<u32> v{ctx->g.out_ptr32, ctx->g.out_col};
+        void* args[] = {&a, &v};
+        CK(cudaLaunchCooperativeKernel((void*)push_kernel<u32>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, 0, ctx->stream));
+    } else {
+        CsrView<int64_t> v{ctx->g.out_ptr64, ctx->g.out_col};
+        void* args[] = {&a, &v};
+        CK(cudaLaunchCooperativeKernel((void*)push_kernel<int64_t>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, 0, ctx->stream));
+    }
+    ctx->launches++;
+    return FORA_OK;
+}
+
+static int launch_residue_stats(fora_ctx* ctx) {
+    const int S = ctx->slots;
+    residue_partial_kernel<<<dim3(ctx->red_blocks, S), RED_THREADS, 0, ctx->stream>>>(ctx->g.n, ctx->residue.p, ctx->part_sum.p, ctx->part_nnz.p);
+    CKL();
+    residue_final_kernel<<<S, 32, 0, ctx->stream>>>(ctx->red_blocks, ctx->part_sum.p, ctx->part_nnz.p, ctx->meta.p->rsum, ctx->meta.p->nnz);
+    CKL();
+    return FORA_OK;
+}
+
+// zero dense state of the first `cnt` slots and install the sources (h_meta->source / qid filled by caller)
+static int init_wave(fora_ctx* ctx, int cnt, int seed_source, const int32_t* d_sources) {
+    const size_t n = (size_t)ctx->g.n;
+    SlotMeta* h = ctx->h_meta;
+    for (int s = 0; s < MAX_SLOTS; ++s) {
+        if (s >= cnt) h->source[s] = -1;
+        h->state[s] = 0; h->active[s] = 0; h->edges[s] = h->vertices[s] = h->levels[s] = 0;
+        h->lastlvl[s] = 0; h->rsum[s] = 0; h->nnz[s] = h->nsrc[s] = h->nwalk[s] = h->hops[s] = h->idx_hits[s] = 0;
+        h->rmax[s] = ctx->p.rmax;
+    }
+    ctx->level_base = 0;
+    int rc = meta_h2d(ctx);
+    if (rc) return rc;
+    if (d_sources) CK(cudaMemcpyAsync(ctx->meta.p->source, d_sources, sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->reserve.p, 0, sizeof(double) * n * cnt, ctx->stream));
+    CK(cudaMemsetAsync(ctx->residue.p, 0, sizeof(double) * n * cnt, ctx->stream));
+    CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
+    push_init_kernel<<<1, MAX_SLOTS, 0, ctx->stream>>>(ctx->g.n, ctx->slots, ctx->meta.p->source, ctx->g.deg, ctx->reserve.p,
+                                                      ctx->residue.p, ctx->front0.p, ctx->ctl.p, seed_source, ctx->meta.p->state);
+    CKL();
+    return FORA_OK;
+}
+
+// one resumable round over the slots flagged in h_meta->active (rmax per slot in h_meta->rmax)
+static int push_round_active(fora_ctx* ctx) {
+    CK(cudaMemcpyAsync(ctx->meta.p->rmax, ctx->h_meta->rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->meta.p->active, ctx->h_meta->active, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
+    const int gx = std::max(1, std::min(ctx->num_sms * 8, (ctx->g.n + 255) / 256));
+    push_seed_kernel<<<dim3(gx, ctx->slots), 256, 0, ctx->stream>>>(ctx->g.n, ctx->g.deg, ctx->residue.p, ctx->meta.p->rmax,
+                                                                   ctx->meta.p->active, ctx->front0.p, ctx->ctl.p);
+    CKL();
+    int rc = launch_push(ctx);
+    if (rc) return rc;
+    return launch_residue_stats(ctx);
+}
+
+// Push phase of a wave of `cnt` FORA queries: plain (algo.h:954) or --balanced (query.h:848-884).
+static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* final_rmax /*[cnt]*/, u64* rounds /*[cnt]*/) {
+    const fora_params& p = ctx->p;
+    SlotMeta* h = ctx->h_meta;
+    int rc;
+    if (!p.balanced) {
+        if ((rc = init_wave(ctx, cnt, 1, d_sources))) return rc;
+        if ((rc = launch_push(ctx))) return rc;
+        if ((rc = launch_residue_stats(ctx))) return rc;
+        for (int s = 0; s < cnt; ++s) { final_rmax[s] = p.rmax; rounds[s] = 1; }
+        return FORA_OK;
+    }
+    if ((rc = init_wave(ctx, cnt, 0, d_sources))) return rc;
+    if ((rc = meta_d2h_sync(ctx))) return rc; // slot states (dangling sources)
+    std::vector<double> rmax(cnt, p.rmax * 8), used(cnt, 0.0), rsum(cnt, 1.0);
+    std::vector<char> done(cnt, 0);
+    std::vector<u64> e0(cnt, 0), v0(cnt, 0), l0(cnt, 0);
+    for (int s = 0; s < cnt; ++s) {
+        rounds[s] = 0;
+        if (h->state[s] != 1) { done[s] = 1; final_rmax[s] = p.rmax; }
+    }
+    for (int iter = 0; iter < 64; ++iter) {
+        bool any = false;
+        for (int s = 0; s < cnt; ++s) {
+            h->active[s] = 0;
+            if (done[s]) continue;
+            // estimated_random_walk_cost, query.h:826-839
+            double est;
+            if (!p.with_idx || rmax[s] >= p.rmax) est = p.omega * rsum[s] * (1 - p.alpha) * p.cost_walk;
+            else est = p.omega * rsum[s] * (1 - p.alpha) * (p.cost_walk / 140);
+            if (!(est > used[s])) {
+                done[s] = 1;
+                final_rmax[s] = rmax[s] * 2; // query.h:878
+                continue;
+            }
+            h->active[s] = 1;
+            h->rmax[s] = rmax[s];
+            e0[s] = h->edges[s]; v0[s] = h->vertices[s]; l0[s] = h->levels[s];
+            any = true;
+        }
+        if (!any) break;
+        if ((rc = push_round_active(ctx))) return rc;
+        if ((rc = meta_d2h_sync(ctx))) return rc;
+        for (int s = 0; s < cnt; ++s) {
+            if (!h->active[s]) continue;
+            used[s] += p.cost_edge * (double)(h->edges[s] - e0[s]) + p.cost_vertex * (double)(h->vertices[s] - v0[s]) +
+                       p.cost_level * (double)(h->levels[s] - l0[s]);
+            rsum[s] = h->rsum[s];
+            rmax[s] /= 2;
+            rounds[s]++;
+        }
+    }
+    for (int s = 0; s < cnt; ++s)
+        if (!done[s]) final_rmax[s] = rmax[s] * 2;
+    return FORA_OK;
+}
+
+// Walk phase of a wave: plan + walk kernels; ppr is accumulated in place into `ppr` ([slots*n],
+// holding the reserve on entry).  round_tag distinguishes the Philox streams of top-k rounds.
+static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_zero_hop, u32 round_tag, const u64* idx_used) {
+    const DeviceGraph& g = ctx->g;
+    const int S = ctx->slots;
+    SlotMeta* m = ctx->meta.p;
+    PlanArgs pa{};
+    pa.n = g.n; pa.alpha = ctx->p.alpha; pa.omega = ctx->p.omega; pa.opt = opt; pa.per_round = per_round;
+    pa.residue = ctx->residue.p; pa.ppr = ppr; pa.rsum = m->rsum; pa.slot_state = m->state;
+    pa.blk_src = ctx->blk_src.p; pa.blk_walk = ctx->blk_walk.p; pa.srcs = ctx->srcs.p; pa.woff = ctx->woff.p;
+    pa.incs = ctx->incs.p; pa.nsrc = m->nsrc; pa.nwalk = m->nwalk;
+    pa.nblk = (g.n + PLAN_THREADS - 1) / PLAN_THREADS;
+    plan_kernel<false><<<dim3(pa.nblk, S), PLAN_THREADS, 0, ctx->stream>>>(pa);
+    CKL();
+    plan_scan_kernel<<<S, 1024, 0, ctx->stream>>>(pa);
+    CKL();
+    plan_kernel<true><<<dim3(pa.nblk, S), PLAN_THREADS, 0, ctx->stream>>>(pa);
+    CKL();
+    const int cgx = std::max<int>(1, std::min<size_t>((size_t)ctx->num_sms * 4, (ctx->chunk_cap + 255) / 256));
+    chunk_start_kernel<<<dim3(cgx, S), 256, 0, ctx->stream>>>(g.n, ctx->woff.p, m->nsrc, m->nwalk, ctx->chunk_first.p, ctx->chunk_cap, m->state);
+    CKL();
+    WalkArgs wa{};
+    wa.n = g.n;
+    wa.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
+    wa.seed_lo = (u32)ctx->seed; wa.seed_hi = (u32)(ctx->seed >> 32);
+    wa.with_idx = ctx->p.with_idx && ctx->has_index;
+    wa.srcs = ctx->srcs.p; wa.woff = ctx->woff.p; wa.incs = ctx->incs.p; wa.nsrc = m->nsrc; wa.nwalk = m->nwalk;
+    wa.chunk_first = ctx->chunk_first.p; wa.chunk_cap = ctx->chunk_cap; wa.slot_state = m->state; wa.qid = m->qid;
+    wa.round_tag = round_tag; wa.ppr = ppr; wa.hops = m->hops; wa.idx_hits = m->idx_hits;
+    wa.idx_off = ctx->idx_off.p; wa.idx_cnt = ctx->idx_cnt.p; wa.idx_dest = ctx->idx_dest.p; wa.idx_used = idx_used;
+    const int wgx = ctx->num_sms * 8;
+    if (g.off32) {
+        CsrView<u32> v{g.out_ptr32, g.out_col};
+        if (no_zero_hop) walk_kernel<u32, true><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
+        else walk_kernel<u32, false><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
+    } else {
+        CsrView<int64_t> v{g.out_ptr64, g.out_col};
+        if (no_zero_hop) walk_kernel<int64_t, true><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
+        else walk_kernel<int64_t, false><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
+    }
+    CKL();
+    return FORA_OK;
+}
+
+static void fill_stat(fora_ctx* ctx, int s, double final_rmax, u64 rounds, fora_query_stat* st) {
+    const SlotMeta* h = ctx->h_meta;
+    memset(st, 0, sizeof *st);
+    st->rsum = h->state[s] == 1 ? h->rsum[s] : 0.0;
+    st->final_rmax = final_rmax;
+    st->n_walks = h->nwalk[s];
+    st->n_idx_hits = h->idx_hits[s];
+    st->walk_hops = h->hops[s];
+    st->edges_pushed = h->edges[s];
+    st->vertices_pushed = h->vertices[s];
+    st->push_levels = h->levels[s];
+    st->push_rounds = rounds;
+    st->n_sources = h->nsrc[s];
+}
+
+// =============================================================================================
+// push test hooks
+// =============================================================================================
+static int require_ready(fora_ctx* ctx, double omega_max) {
+    if (!ctx) return FORA_EINVAL;
+    if (!ctx->params_set) return ctx->fail(FORA_EINVAL, "fora_params_set has not been called");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return ctx->fail(FORA_ECUDA, cudaGetErrorString(e));
+    return ensure_slots(ctx, omega_max);
+}
+
+static int download_fwd(fora_ctx* ctx, int slot, double* reserve, double* residue) {
+    const size_t n = (size_t)ctx->g.n;
+    if (reserve) CK(cudaMemcpyAsync(reserve, ctx->reserve.p + n * slot, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (residue) CK(cudaMemcpyAsync(residue, ctx->residue.p + n * slot, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+
+extern "C" int fora_push_only(fora_ctx* ctx, int32_t source, double rmax, double* reserve, double* residue, double* rsum,
+                              fora_query_stat* stat) {
+    int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
+    if (rc) return rc;
+    if (source < 0 || source >= ctx->g.n) return ctx->fail(FORA_EINVAL, "source out of range");
+    const double keep = ctx->p.rmax;
+    const int keep_bal = ctx->p.balanced;
+    ctx->p.rmax = rmax;
+    ctx->p.balanced = 0;
+    ctx->h_meta->source[0] = source;
+    ctx->h_meta->qid[0] = 0;
+    double fr;
+    u64 rounds;
+    rc = push_wave(ctx, 1, nullptr, &fr, &rounds);
+    ctx->p.rmax = keep;
+    ctx->p.balanced = keep_bal;
+    if (rc) return rc;
+    if ((rc = meta_d2h_sync(ctx))) return rc;
+    if (rsum) *rsum = ctx->h_meta->state[0] == 1 ? ctx->h_meta->rsum[0] : 0.0;
+    if (stat) fill_stat(ctx, 0, rmax, 1, stat);
+    ctx->session_source = -1;
+    return download_fwd(ctx, 0, reserve, residue);
+}
+
+extern "C" int fora_push_begin(fora_ctx* ctx, int32_t source) {
+    int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
+    if (rc) return rc;
+    if (source < 0 || source >= ctx->g.n) return ctx->fail(FORA_EINVAL, "source out of range");
+    ctx->h_meta->source[0] = source;
+    ctx->h_meta->qid[0] = 0;
+    if ((rc = init_wave(ctx, 1, 0, nullptr))) return rc;
+    if ((rc = meta_d2h_sync(ctx))) return rc;
+    ctx->session_source = source;
+    return FORA_OK;
+}
+
+extern "C" int fora_push_round(fora_ctx* ctx, double rmax, double* reserve, double* residue, double* rsum, fora_query_stat* stat) {
+    if (!ctx) return FORA_EINVAL;
+    if (ctx->session_source < 0) return ctx->fail(FORA_EINVAL, "fora_push_begin has not been called");
+    CK(cudaSetDevice(ctx->device));
+    SlotMeta* h = ctx->h_meta;
+    int rc;
+    if (h->state[0] == 1) {
+        for (int s = 0; s < MAX_SLOTS; ++s) h->active[s] = 0;
+        h->active[0] = 1;
+        h->rmax[0] = rmax;
+        if ((rc = push_round_active(ctx))) return rc;
+    } else if ((rc = launch_residue_stats(ctx))) return rc;
+    if ((rc = meta_d2h_sync(ctx))) return rc;
+    if (rsum) *rsum = h->state[0] == 1 ? h->rsum[0] : 0.0;
+    if (stat) fill_stat(ctx, 0, rmax, 1, stat);
+    return download_fwd(ctx, 0, reserve, residue);
+}
+
+// =============================================================================================
+// walks test hook / Monte-Carlo building block
+// =============================================================================================
+static int launch_bulk(fora_ctx* ctx, const BulkArgs& ba, int no_zero_hop) {
+    const DeviceGraph& g = ctx->g;
+    const int gx = (int)std::max<u64>(1, std::min<u64>((u64)ctx->num_sms * 8, (ba.total + WALK_THREADS - 1) / WALK_THREADS));
+    if (g.off32) {
+        CsrView<u32> v{g.out_ptr32, g.out_col};
+        if (no_zero_hop) bulk_walk_kernel<u32, true><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
+        else bulk_walk_kernel<u32, false><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
+    } else {
+        CsrView<int64_t> v{g.out_ptr64, g.out_col};
+        if (no_zero_hop) bulk_walk_kernel<int64_t, true><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
+        else bulk_walk_kernel<int64_t, false><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
+    }
+    CKL();
+    return FORA_OK;
+}
+
+extern "C" int fora_random_walks(fora_ctx* ctx, int32_t start, int64_t count, int no_zero_hop, int32_t* dest, uint64_t* hops) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    if (start < 0 || start >= ctx->g.n || count < 0) return ctx->fail(FORA_EINVAL, "bad start/count");
+    CK(cudaSetDevice(ctx->device));
+    CK(ctx->scratch32.ensure((size_t)std::max<int64_t>(count, 1)));
+    CK(ctx->scratch64.ensure(1));
+    CK(cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(u64), ctx->stream));
+    BulkArgs ba{};
+    ba.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
+    ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
+    ba.key_tag = 0x77a1c5u;
+    ba.single = start; ba.total = (u64)count; ba.dest = ctx->scratch32.p; ba.counts = nullptr; ba.hops = ctx->scratch64.p;
+    int rc = launch_bulk(ctx, ba, no_zero_hop);
+    if (rc) return rc;
+    if (dest) CK(cudaMemcpyAsync(dest, ctx->scratch32.p, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hops) CK(cudaMemcpyAsync(hops, ctx->scratch64.p, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+
+extern "C" int fora_compute_ppr(fora_ctx* ctx, const double* reserve, const double* residue, double rsum, double* ppr,
+                                fora_query_stat* stat) {
+    int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
+    if (rc) return rc;
+    if (!reserve || !residue || !ppr) return ctx->fail(FORA_EINVAL, "null vector");
+    const size_t n = (size_t)ctx->g.n;
+    SlotMeta* h = ctx->h_meta;
+    memset(h, 0, sizeof *h);
+    for (int s = 0; s < MAX_SLOTS; ++s) h->source[s] = -1;
+    h->source[0] = 0;
+    h->state[0] = rsum == 0.0 ? 2 : 1; // query.h:267-268: rsum == 0 -> ppr = reserve only
+    h->rsum[0] = rsum;
+    if ((rc = meta_h2d(ctx))) return rc;
+    CK(cudaMemcpyAsync(ctx->reserve.p, reserve, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->residue.p, residue, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = walk_wave(ctx, ctx->reserve.p, 0, ctx->p.opt, ctx->p.opt, 0, nullptr))) return rc;
+    if ((rc = meta_d2h_sync(ctx))) return rc;
+    if (stat) fill_stat(ctx, 0, ctx->p.rmax, 0, stat);
+    CK(cudaMemcpyAsync(ppr, ctx->reserve.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->session_source = -1;
+    return FORA_OK;
+}
+
+// =============================================================================================
+// queries
+// =============================================================================================
+static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, const int32_t* d_sources, int32_t n_q, double* ppr,
+                            fora_query_stat* stats, fora_batch_timing* timing) {
+    int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
+    if (rc) return rc;
+    if (n_q < 0 || (!h_sources && !d_sources && n_q)) return ctx->fail(FORA_EINVAL, "bad sources");
+    if (algo != FORA_ALGO_FORA && algo != FORA_ALGO_FWDPUSH && algo != FORA_ALGO_MC)
+        return ctx->fail(FORA_EINVAL, "algo not supported by fora_query_batch (bippr: see fora_bippr_query)");
+    const size_t n = (size_t)ctx->g.n;
+    const int S = ctx->slots;
+    ctx->session_source = -1;
+    const u64 launches0 = ctx->launches;
+    float push_ms = 0, walk_ms = 0, copy_ms = 0;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    std::vector<double> fr(S);
+    std::vector<u64> rounds(S);
+    SlotMeta* h = ctx->h_meta;
+    for (int32_t q0 = 0; q0 < n_q; q0 += S) {
+        const int cnt = std::min<int32_t>(S, n_q - q0);
+        for (int s = 0; s < cnt; ++s) {
+            if (h_sources) {
+                if (h_sources[q0 + s] < 0 || h_sources[q0 + s] >= ctx->g.n) return ctx->fail(FORA_EINVAL, "source out of range");
+                h->source[s] = h_sources[q0 + s];
+            } else h->source[s] = 0;
+            h->qid[s] = (u32)(q0 + s);
+        }
+        CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        if (algo == FORA_ALGO_FORA) {
+            if ((rc = push_wave(ctx, cnt, d_sources ? d_sources + q0 : nullptr, fr.data(), rounds.data()))) return rc;
+            CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+            if ((rc = walk_wave(ctx, ctx->reserve.p, 0, ctx->p.opt, ctx->p.opt, 0, nullptr))) return rc;
+        } else if (algo == FORA_ALGO_FWDPUSH) { // query.h:1503-1508: push at config.rmax, ppr = reserve
+            const int keep = ctx->p.balanced;
+            ctx->p.balanced = 0;
+            rc = push_wave(ctx, cnt, d_sources ? d_sources + q0 : nullptr, fr.data(), rounds.data());
+            ctx->p.balanced = keep;
+            if (rc) return rc;
+            CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+        } else { // Monte-Carlo, query.h:16-43: omega walks from the source, ppr = count/omega
+            if ((rc = init_wave(ctx, cnt, 0, d_sources ? d_sources + q0 : nullptr))) return rc;
+            if ((rc = meta_d2h_sync(ctx))) return rc;
+            CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+            CK(ctx->counts.ensure(n));
+            const u64 nw = (u64)ceil(ctx->p.omega); // for(i=0; i<omega; i++), query.h:25
+            for (int s = 0; s < cnt; ++s) {
+                CK(cudaMemsetAsync(ctx->counts.p, 0, sizeof(u64) * n, ctx->stream));
+                BulkArgs ba{};
+                ba.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
+                ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
+                ba.key_tag = 0x4d430000u + h->qid[s];
+                ba.single = h->source[s]; ba.total = nw; ba.dest = nullptr; ba.counts = ctx->counts.p;
+                ba.hops = &ctx->meta.p->hops[s];
+                if (d_sources) { // source id lives on the device: fetch it (tiny)
+                    int32_t sv;
+                    CK(cudaMemcpyAsync(&sv, d_sources + q0 + s, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream));
+                    ba.single = sv;
+                }
+                if ((rc = launch_bulk(ctx, ba, 0))) return rc;
+                counts_to_ppr_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->g.n, ctx->counts.p, ctx->p.omega, ctx->reserve.p + n * s);
+                CKL();
+                h->nwalk[s] = nw;
+            }
+            CK(cudaMemcpyAsync(ctx->meta.p->nwalk, h->nwalk, sizeof(u64) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+        if (ppr) CK(cudaMemcpyAsync(ppr + (size_t)q0 * n, ctx->reserve.p, sizeof(double) * n * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaEventRecord(ctx->ev[4], ctx->stream));
+        if ((rc = meta_d2h_sync(ctx))) return rc;
+        if (stats)
+            for (int s = 0; s < cnt; ++s) fill_stat(ctx, s, algo == FORA_ALGO_FORA ? fr[s] : ctx->p.rmax, algo == FORA_ALGO_MC ? 0 : rounds[s], &stats[q0 + s]);
+        float t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); push_ms += t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3])); walk_ms += t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4])); copy_ms += t;
+    }
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[5]));
+    if (timing) {
+        memset(timing, 0, sizeof *timing);
+        CK(cudaEventElapsedTime(&timing->total_ms, ctx->ev[0], ctx->ev[5]));
+        timing->push_ms = push_ms; timing->walk_ms = walk_ms; timing->copy_ms = copy_ms;
+        timing->kernel_launches = ctx->launches - launches0;
+    }
+    return FORA_OK;
+}
+
+extern "C" int fora_query_batch(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, double* ppr,
+                                fora_query_stat* stats, fora_batch_timing* timing) {
+    return query_batch_impl(ctx, algo, sources, nullptr, n_q, ppr, stats, timing);
+}
+extern "C" int fora_query_batch_device(fora_ctx* ctx, int algo, const int32_t* d_sources, int32_t n_q, fora_query_stat* stats,
+                                       fora_batch_timing* timing) {
+    return query_batch_impl(ctx, algo, nullptr, d_sources, n_q, nullptr, stats, timing);
+}
+extern "C" void* fora_device_ppr(fora_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= ctx->alloc_slots) return nullptr;
+    return ctx->reserve.p + (size_t)ctx->g.n * slot;
+}
+
+// =============================================================================================
+// walk index
+// =============================================================================================
+extern "C" int fora_index_info(fora_ctx* ctx, uint64_t* offsets, uint64_t* counts, uint64_t* total) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    if (!ctx->params_set || !offsets || !counts) return ctx->fail(FORA_EINVAL, "params / outputs missing");
+    CK(cudaSetDevice(ctx->device));
+    const int32_t n = ctx->g.n;
+    std::vector<int32_t> deg((size_t)n);
+    CK(cudaMemcpy(deg.data(), ctx->g.deg, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    // build.h:325-334 -- host arithmetic in the reference's expression order (bit-exact counts)
+    const fora_params& p = ctx->p;
+    u64 tuned = 0;
+    for (int32_t v = 0; v < n; ++v) {
+        const size_t d = (size_t)deg[v];
+        unsigned long num_rw;
+        if (p.opt) num_rw = (unsigned long)ceil(d * p.rmax * (1 - p.alpha) * p.omega);
+        else num_rw = (unsigned long)ceil(d * p.rmax * p.omega);
+        offsets[v] = tuned;
+        counts[v] = num_rw;
+        tuned += num_rw;
+    }
+    if (total) *total = tuned;
+    return FORA_OK;
+}
+
+extern "C" int fora_index_build(fora_ctx* ctx, const uint64_t* offsets, const uint64_t* counts, int32_t v_begin, int32_t v_end,
+                                int32_t* dest) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    if (!offsets || !counts || !dest || v_begin < 0 || v_end > ctx->g.n || v_begin > v_end) return ctx->fail(FORA_EINVAL, "bad range");
+    CK(cudaSetDevice(ctx->device));
+    const u64 nseg = (u64)(v_end - v_begin);
+    if (nseg == 0) return FORA_OK;
+    const u64 base = offsets[v_begin];
+    const u64 total = offsets[v_end - 1] + counts[v_end - 1] - base;
+    if (total == 0) return FORA_OK;
+    std::vector<u64> rel(nseg + 1);
+    for (u64 i = 0; i < nseg; ++i) rel[i] = offsets[v_begin + i] - base;
+    rel[nseg] = total;
+    CK(ctx->scratch64.ensure(nseg + 2));
+    CK(ctx->scratch32.ensure(total));
+    CK(cudaMemcpyAsync(ctx->scratch64.p + 1, rel.data(), sizeof(u64) * (nseg + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(u64), ctx->stream));
+    BulkArgs ba{};
+    ba.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
+    ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
+    ba.key_tag = 0x1d800000u;
+    ba.seg_off = ctx->scratch64.p + 1; ba.v_begin = v_begin; ba.single = -1; ba.nseg = nseg; ba.total = total;
+    ba.dest = ctx->scratch32.p; ba.counts = nullptr; ba.hops = ctx->scratch64.p;
+    int rc = launch_bulk(ctx, ba, ctx->p.opt); // build.h:347-350
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(dest, ctx->scratch32.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+
+extern "C" int fora_index_upload(fora_ctx* ctx, const uint64_t* offsets, const uint64_t* counts, const int32_t* dest, uint64_t len) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    if (!offsets || !counts || (!dest && len)) return ctx->fail(FORA_EINVAL, "null index arrays");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->g.n;
+    if (n && offsets[n - 1] + counts[n - 1] > len) return ctx->fail(FORA_EINVAL, "index info exceeds destination array");
+    CK(ctx->idx_off.ensure(n));
+    CK(ctx->idx_cnt.ensure(n));
+    CK(ctx->idx_dest.ensure(std::max<size_t>(len, 1)));
+    CK(cudaMemcpyAsync(ctx->idx_off.p, offsets, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->idx_cnt.p, counts, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->idx_dest.p, dest, sizeof(int32_t) * len, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->has_index = true;
+    return FORA_OK;
+}
+
+// =============================================================================================
+// top-k of a dense vector and power iteration live in topk.cuh
+// =============================================================================================
+extern "C" int fora_topk_of(fora_ctx* ctx, const double* ppr, uint32_t k, int32_t* nodes, double* values) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    if (!ppr || !nodes || !values || k == 0) return ctx->fail(FORA_EINVAL, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->g.n;
+    CK(ctx->scratchd.ensure(n));
+    CK(cudaMemcpyAsync(ctx->scratchd.p, ppr, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    TopkWork tw;
+    cudaError_t e = topk_device(ctx->stream, ctx->num_sms, ctx->scratchd.p, ctx->g.n, k, nodes, values, &ctx->launches);
+    if (e != cudaSuccess) return ctx->fail(FORA_ECUDA, std::string("topk: ") + cudaGetErrorString(e));
+    (void)tw;
+    return FORA_OK;
+}
+
+extern "C" int fora_power_iteration(fora_ctx* ctx, int32_t source, int iters, double* ppr) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    if (source < 0 || source >= ctx->g.n || iters < 0 || !ppr) return ctx->fail(FORA_EINVAL, "bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->g.n;
+    CK(ctx->scratchd.ensure(3 * n + 2));
+    cudaError_t e;
+    if (ctx->g.off32) e = power_iteration_device<u32>(ctx->stream, ctx->num_sms, CsrView<u32>{ctx->g.out_ptr32, ctx->g.out_col}, ctx->g.n, source, iters, ctx->p.alpha, ctx->scratchd.p, &ctx->launches);
+    else e = power_iteration_device<int64_t>(ctx->stream, ctx->num_sms, CsrView<int64_t>{ctx->g.out_ptr64, ctx->g.out_col}, ctx->g.n, source, iters, ctx->p.alpha, ctx->scratchd.p, &ctx->launches);
+    if (e != cudaSuccess) return ctx->fail(FORA_ECUDA, std::string("power iteration: ") + cudaGetErrorString(e));
+    CK(cudaMemcpyAsync(ppr, ctx->scratchd.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+
+// =============================================================================================
+// not yet wired (fail loudly rather than fall back)
+// =============================================================================================
+extern "C" int fora_reverse_push(fora_ctx* ctx, int32_t, double, double*, double*) {
+    return ctx ? ctx->fail(FORA_EINVAL, "fora_reverse_push: not implemented in this build") : FORA_EINVAL;
+}
+extern "C" int fora_topk_batch(fora_ctx* ctx, int, const int32_t*, int32_t, uint32_t, int32_t*, double*, int32_t*,
+                               fora_query_stat*, fora_batch_timing*) {
+    return ctx ? ctx->fail(FORA_EINVAL, "fora_topk_batch: not implemented in this build") : FORA_EINVAL;
+}

@@ -1,0 +1,224 @@
+// fora_b200/csrc/host_util.cpp -- host-side parts of the C ABI (no GPU work): text loader,
+// CSR construction, synthetic graph generator, parameter derivation.
+//
+// These replace Graph::init_nm / init_graph (/root/reference/graph.h:48-64,89-163) and the
+// *_setting functions (/root/reference/algo.h:442-496).  Arithmetic follows the reference's
+// expression order so the doubles are bit-identical (checked against the reference in tests/).
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#include "fora_b200.h"
+
+extern "C" {
+
+int fora_host_read_attribute(const char* path, int32_t* n, int64_t* m) {
+    // graph.h:48-64: skip to '=', read n; skip to '=', read m.
+    FILE* f = fopen(path, "r");
+    if (!f) return FORA_EIO;
+    int c;
+    long long mm = 0;
+    int nn = 0;
+    while ((c = fgetc(f)) != EOF && c != '=') {}
+    if (fscanf(f, "%d", &nn) != 1) { fclose(f); return FORA_EIO; }
+    while ((c = fgetc(f)) != EOF && c != '=') {}
+    if (fscanf(f, "%lld", &mm) != 1) { fclose(f); return FORA_EIO; }
+    fclose(f);
+    *n = nn;
+    *m = mm;
+    return FORA_OK;
+}
+
+// Whitespace-separated decimal pairs, as fscanf("%d%d") reads them (graph.h:154); the whole file is
+// read once and scanned by hand (the reference's fscanf loop dominates load time at 1e9 edges).
+int64_t fora_host_read_edges(const char* path, int32_t n, int32_t* src, int32_t* dst) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return FORA_EIO;
+    const size_t BUF = 1 << 24;
+    std::vector<char> buf(BUF);
+    int64_t kept = 0;
+    long long val = 0;
+    bool in_num = false, neg = false, have_first = false;
+    long long first = 0;
+    size_t got;
+    auto flush = [&](long long v) -> int {
+        if (!have_first) { first = v; have_first = true; return 0; }
+        have_first = false;
+        if (!(first < n) || !(v < n)) return 1; // graph.h:155-156
+        if (first == v) return 0;                // graph.h:157
+        if (src) { src[kept] = (int32_t)first; dst[kept] = (int32_t)v; }
+        ++kept;
+        return 0;
+    };
+    bool bad = false;
+    while (!bad && (got = fread(buf.data(), 1, BUF, f)) > 0) {
+        for (size_t i = 0; i < got; ++i) {
+            const char ch = buf[i];
+            if (ch >= '0' && ch <= '9') { val = val * 10 + (ch - '0'); in_num = true; }
+            else if (ch == '-' && !in_num) { neg = true; }
+            else {
+                if (in_num) { if (flush(neg ? -val : val)) { bad = true; break; } }
+                val = 0; in_num = false; neg = false;
+            }
+        }
+    }
+    if (!bad && in_num && flush(neg ? -val : val)) bad = true;
+    fclose(f);
+    return bad ? (int64_t)FORA_ERANGE : kept;
+}
+
+// Stable counting sort == push_back in file order (graph.h:158-159).
+int fora_host_csr_from_edges(int32_t n, int64_t ne, const int32_t* src, const int32_t* dst, int64_t* out_ptr,
+                             int32_t* out_col, int64_t* in_ptr, int32_t* in_col) {
+    if (n <= 0 || ne < 0) return FORA_EINVAL;
+    std::fill(out_ptr, out_ptr + n + 1, 0);
+    if (in_ptr) std::fill(in_ptr, in_ptr + n + 1, 0);
+    for (int64_t e = 0; e < ne; ++e) {
+        const int32_t s = src[e], d = dst[e];
+        if ((uint32_t)s >= (uint32_t)n || (uint32_t)d >= (uint32_t)n) return FORA_ERANGE;
+        if (s == d) continue;
+        out_ptr[s + 1]++;
+        if (in_ptr) in_ptr[d + 1]++;
+    }
+    for (int32_t i = 0; i < n; ++i) {
+        out_ptr[i + 1] += out_ptr[i];
+        if (in_ptr) in_ptr[i + 1] += in_ptr[i];
+    }
+    auto fill_dir = [&](const int32_t* key, const int32_t* val, const int64_t* ptr, int32_t* col) {
+        std::vector<int64_t> pos(ptr, ptr + n);
+        for (int64_t e = 0; e < ne; ++e) {
+            if (src[e] == dst[e]) continue;
+            col[pos[key[e]]++] = val[e];
+        }
+    };
+    if (in_ptr && in_col) {
+        std::thread t([&] { fill_dir(dst, src, in_ptr, in_col); });
+        fill_dir(src, dst, out_ptr, out_col);
+        t.join();
+    } else {
+        fill_dir(src, dst, out_ptr, out_col);
+    }
+    return FORA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Deterministic synthetic directed power-law graph: Chung-Lu style with a shifted
+// power law weight (rank + shift)^(-1/(exponent-1)) on both endpoints (independent random
+// relabelling of out- and in-ranks), `dangling_frac` of the vertices never emit an edge, self loops
+// re-drawn so exactly m edges are kept, duplicates allowed.  Edge e is a pure function of
+// (seed, e / CHUNK, e % CHUNK): the output does not depend on the thread count.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct SplitMix {
+    uint64_t s;
+    explicit SplitMix(uint64_t seed) : s(seed) {}
+    inline uint64_t next() {
+        uint64_t z = (s += 0x9e3779b97f4a7c15ULL);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        return z ^ (z >> 31);
+    }
+    inline double unit() { return (double)(next() >> 11) * (1.0 / 9007199254740992.0); }
+};
+void permutation(std::vector<int32_t>& p, uint64_t seed) {
+    SplitMix r(seed);
+    for (size_t i = p.size(); i > 1; --i) {
+        size_t j = (size_t)(r.next() % i);
+        std::swap(p[i - 1], p[j]);
+    }
+}
+} // namespace
+
+int64_t fora_host_synth_edges(int32_t n, int64_t m, uint64_t seed, double exponent, double dangling_frac, int32_t* src,
+                              int32_t* dst) {
+    if (n < 4 || m < 1 || exponent <= 1.0) return FORA_EINVAL;
+    const double beta = 1.0 / (exponent - 1.0);
+    const double shift = 50.0;
+    const double e1 = 1.0 - beta;
+    // dangling set = the first n_d entries of a random permutation
+    std::vector<int32_t> perm_out(n), perm_in(n);
+    for (int32_t i = 0; i < n; ++i) perm_out[i] = perm_in[i] = i;
+    permutation(perm_out, seed * 3 + 1);
+    permutation(perm_in, seed * 3 + 2);
+    int32_t n_d = (int32_t)(dangling_frac * n);
+    if (n_d > n - 2) n_d = n - 2;
+    const int32_t n_src = n - n_d; // out-ranks map onto perm_out[n_d ...]
+    auto sample_rank = [&](double u, int32_t cnt) -> int32_t {
+        const double a = pow(shift, e1), b = pow((double)cnt + shift, e1);
+        double x = pow(u * (b - a) + a, 1.0 / e1) - shift;
+        int32_t r = (int32_t)x;
+        if (r < 0) r = 0;
+        if (r >= cnt) r = cnt - 1;
+        return r;
+    };
+    const int64_t CHUNK = 1 << 20;
+    const int64_t nchunks = (m + CHUNK - 1) / CHUNK;
+    unsigned T = std::thread::hardware_concurrency();
+    if (T == 0) T = 1;
+    if ((int64_t)T > nchunks) T = (unsigned)nchunks;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < T; ++t) {
+        th.emplace_back([&, t] {
+            for (int64_t c = t; c < nchunks; c += T) {
+                // chunk streams must not be shifted copies of each other: hash (seed, chunk) first
+                SplitMix h(seed ^ (0xA0761D6478BD642FULL * (uint64_t)(c + 1)));
+                h.next();
+                SplitMix r(h.next() ^ (uint64_t)c);
+                const int64_t lo = c * CHUNK, hi = std::min(m, lo + CHUNK);
+                for (int64_t e = lo; e < hi; ++e) {
+                    const int32_t s = perm_out[n_d + sample_rank(r.unit(), n_src)];
+                    int32_t d;
+                    do { d = perm_in[sample_rank(r.unit(), n)]; } while (d == s);
+                    src[e] = s;
+                    dst[e] = d;
+                }
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    return m;
+}
+
+// ---------------------------------------------------------------------------------------------
+// algo.h:442-496
+// ---------------------------------------------------------------------------------------------
+int fora_host_setting(int which, int32_t n, int64_t m, double epsilon, double delta, double pfail, double alpha, int opt,
+                      double rmax_scale, double* rmax_out, double* omega_out) {
+    double rmax = 0.0, omega = 0.0;
+    switch (which) {
+        case 0: // fora_setting, algo.h:455-463
+            rmax = epsilon * sqrt(delta / 3 / m / log(2 / pfail));
+            if (opt) rmax *= rmax_scale / (1 - alpha);
+            else rmax *= rmax_scale;
+            omega = (2 + epsilon) * log(2 / pfail) / delta / epsilon / epsilon;
+            break;
+        case 1: // fora_topk_setting, algo.h:466-474
+            rmax = epsilon * sqrt(delta / 3 / m / log(2 / pfail));
+            rmax *= sqrt(1.0 * m * rmax) * rmax_scale * 3;
+            omega = (2 + epsilon) * log(2 / pfail) / delta / epsilon / epsilon;
+            break;
+        case 2: // montecarlo_setting, algo.h:477-483
+            omega = 3 * log(2 / pfail) / epsilon / epsilon / delta;
+            break;
+        case 3: // bippr_setting, algo.h:442-447
+            rmax = epsilon * sqrt(m * 1.0 * delta / 3.0 / log(2.0 / pfail));
+            rmax *= rmax_scale;
+            omega = rmax * 3 * log(2.0 / pfail) / delta / epsilon / epsilon;
+            break;
+        case 4: // fwdpush_setting, algo.h:495
+            rmax = rmax_scale * delta * epsilon * n / m;
+            break;
+        default:
+            return FORA_EINVAL;
+    }
+    if (rmax_out) *rmax_out = rmax;
+    if (omega_out) *omega_out = omega;
+    return FORA_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,404 @@
+// fora_b200/csrc/walk.cuh -- residue-seeded Monte-Carlo phase and walk-index kernels on sm_100a.
+//
+// Replaces compute_ppr_with_fwdidx / _opt (/root/reference/query.h:255-413), the walk loops of
+// random_walk / random_walk_no_zero_hop (algo.h:124-166), montecarlo_query (query.h:16-43) and
+// the index build loop (build.h:344-354).
+//
+//   plan      per source v with residue r:  n_v = ceil(r/rsum*N), inc_v = (r/rsum*N/n_v)*rsum/N,
+//             N = (ull)(omega*rsum)  -- the reference's expressions, evaluated in the same order in
+//             IEEE double on the device (query.h:270,314-317; opt: 349,363-370), compacted in
+//             ascending vertex order with an exclusive prefix sum of n_v (two deterministic passes)
+//   walk      one walker per thread; a thread that finishes a walk immediately starts its next one
+//             (lanes never idle waiting for the longest walk of the warp); Philox4x32-10 keyed by
+//             (seed, query id, round) with counter (walk index within source, draw block, source),
+//             so destinations do not depend on scheduling, slot count or GPU count; row offsets and
+//             neighbours through the read-only path; ppr[dest] += inc_v as fp64 RED.
+#pragma once
+#include "common.cuh"
+
+namespace fora {
+
+constexpr int PLAN_THREADS = 1024;
+constexpr int WALK_THREADS = 256;
+constexpr int WALK_CHUNK = 2048; // walks per chunk (8 per thread)
+
+struct PlanArgs {
+    int32_t n;
+    double alpha, omega;
+    int opt;        // --opt: rsum *= (1-alpha), ppr[v] += alpha*r, r *= (1-alpha)  (query.h:349,363-364)
+    int per_round;  // top-k rounds: n_v = ceil(r*omega), inc = (r*omega/n_v)/omega     (query.h:568-571)
+    const double* __restrict__ residue; // [slots*n]
+    double* ppr;                        // [slots*n] in/out: holds reserve on entry (may alias reserve)
+    const double* __restrict__ rsum;    // [slots]
+    const int32_t* __restrict__ slot_state;
+    // outputs, per slot
+    u32* __restrict__ blk_src;   // [slots*nblk]
+    u64* __restrict__ blk_walk;  // [slots*nblk]
+    int32_t* __restrict__ srcs;  // [slots*n]
+    u64* __restrict__ woff;      // [slots*(n+1)]
+    double* __restrict__ incs;   // [slots*n]
+    u64* __restrict__ nsrc;      // [slots]
+    u64* __restrict__ nwalk;     // [slots]
+    int nblk;
+};
+
+// n_v and inc_v for one source; identical expression order to query.h:314-317 (and 349,400-404).
+__device__ __forceinline__ void plan_one(const PlanArgs& a, double r, double check_rsum, u64 num_random_walk, u64* n_v,
+                                         double* inc) {
+    if (a.per_round) { // query.h:567-571
+        const double num = ceil(__dmul_rn(r, a.omega));
+        *n_v = (u64)num;
+        const double a_s = __ddiv_rn(__dmul_rn(r, a.omega), (double)*n_v);
+        *inc = __ddiv_rn(a_s, a.omega);
+        return;
+    }
+    const double q = __dmul_rn(__ddiv_rn(r, check_rsum), (double)num_random_walk);
+    *n_v = (u64)ceil(q);
+    const double a_s = __ddiv_rn(q, (double)*n_v);
+    *inc = __ddiv_rn(__dmul_rn(a_s, check_rsum), (double)num_random_walk);
+}
+
+// pass 1 (count) and pass 2 (fill) share the per-vertex evaluation; FILL selects the pass.
+template <bool FILL>
+__global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(PlanArgs a) {
+    __shared__ u32 s_wsrc[PLAN_THREADS / WARP];
+    __shared__ u64 s_wwalk[PLAN_THREADS / WARP];
+    const int slot = blockIdx.y;
+    if (a.slot_state[slot] == 0) return;
+    const int v = blockIdx.x * PLAN_THREADS + threadIdx.x;
+    const size_t gi = (size_t)slot * a.n + (v < a.n ? v : 0);
+    double check_rsum = a.rsum[slot];
+    if (a.opt) check_rsum = __dmul_rn(check_rsum, 1.0 - a.alpha);
+    const u64 num_random_walk = (u64)__dmul_rn(a.omega, check_rsum);
+
+    double r = 0.0;
+    u64 n_v = 0;
+    double inc = 0.0;
+    if (v < a.n && a.slot_state[slot] == 1) {
+        r = a.residue[gi];
+        if (r > 0.0) {
+            double rw = r;
+            if (a.opt) rw = __dmul_rn(r, 1.0 - a.alpha);
+            plan_one(a, rw, check_rsum, num_random_walk, &n_v, &inc);
+        }
+    }
+    const u32 flag = r > 0.0;
+    // block-wide exclusive scan of (flag, n_v): warp scan + scan of warp totals
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const u32 fs = warp_incl_scan(flag);
+    const u64 ws = warp_incl_scan64(n_v);
+    if (lane == 31) {
+        s_wsrc[w] = fs;
+        s_wwalk[w] = ws;
+    }
+    __syncthreads();
+    if (w == 0) {
+        u32 x = s_wsrc[lane];
+        u64 y = s_wwalk[lane];
+        const u32 xi = warp_incl_scan(x);
+        const u64 yi = warp_incl_scan64(y);
+        s_wsrc[lane] = xi - x;
+        s_wwalk[lane] = yi - y;
+        if (!FILL && lane == 31) {
+            a.blk_src[(size_t)slot * a.nblk + blockIdx.x] = xi;
+            a.blk_walk[(size_t)slot * a.nblk + blockIdx.x] = yi;
+        }
+    }
+    if (!FILL) return;
+    __syncthreads();
+    if (v < a.n && flag) {
+        const size_t pos = (size_t)a.blk_src[(size_t)slot * a.nblk + blockIdx.x] + s_wsrc[w] + (fs - flag);
+        const u64 wo = a.blk_walk[(size_t)slot * a.nblk + blockIdx.x] + s_wwalk[w] + (ws - n_v);
+        a.srcs[(size_t)slot * a.n + pos] = v;
+        a.woff[(size_t)slot * (a.n + 1) + pos] = wo;
+        a.incs[(size_t)slot * a.n + pos] = inc;
+        if (a.opt || a.per_round == 2) a.ppr[gi] += __dmul_rn(r, a.alpha); // query.h:363 / 562
+    }
+}
+
+// exclusive scan of the per-block totals of one slot (in place) + totals; one block per slot.
+__global__ void __launch_bounds__(1024) plan_scan_kernel(PlanArgs a) {
+    __shared__ u32 s_x[32];
+    __shared__ u64 s_y[32];
+    __shared__ u32 s_cx;
+    __shared__ u64 s_cy;
+    const int slot = blockIdx.x;
+    if (a.slot_state[slot] == 0) return;
+    u32* bs = a.blk_src + (size_t)slot * a.nblk;
+    u64* bw = a.blk_walk + (size_t)slot * a.nblk;
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_cx = 0; s_cy = 0; }
+    __syncthreads();
+    for (int base = 0; base < a.nblk; base += 1024) {
+        const int i = base + threadIdx.x;
+        const u32 x = i < a.nblk ? bs[i] : 0;
+        const u64 y = i < a.nblk ? bw[i] : 0;
+        const u32 xi = warp_incl_scan(x);
+        const u64 yi = warp_incl_scan64(y);
+        if (lane == 31) { s_x[w] = xi; s_y[w] = yi; }
+        __syncthreads();
+        if (w == 0) {
+            const u32 tx = s_x[lane];
+            const u64 ty = s_y[lane];
+            const u32 txi = warp_incl_scan(tx);
+            const u64 tyi = warp_incl_scan64(ty);
+            s_x[lane] = txi - tx;
+            s_y[lane] = tyi - ty;
+        }
+        __syncthreads();
+        const u32 cx = s_cx;
+        const u64 cy = s_cy;
+        if (i < a.nblk) {
+            bs[i] = cx + s_x[w] + (xi - x);
+            bw[i] = cy + s_y[w] + (yi - y);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) {
+            s_cx = cx + s_x[w] + xi;
+            s_cy = cy + s_y[w] + yi;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        a.nsrc[slot] = s_cx;
+        a.nwalk[slot] = s_cy;
+        a.woff[(size_t)slot * (a.n + 1) + s_cx] = s_cy; // sentinel
+    }
+}
+
+// chunk c of slot s starts inside source chunk_first[c]: largest i with woff[i] <= c*WALK_CHUNK.
+__global__ void __launch_bounds__(256) chunk_start_kernel(int32_t n, const u64* __restrict__ woff,
+                                                          const u64* __restrict__ nsrc, const u64* __restrict__ nwalk,
+                                                          u32* __restrict__ chunk_first, size_t chunk_cap,
+                                                          const int32_t* __restrict__ slot_state) {
+    const int slot = blockIdx.y;
+    if (slot_state[slot] != 1) return;
+    const u64 W = nwalk[slot];
+    const u64 nchunks = (W + WALK_CHUNK - 1) / WALK_CHUNK;
+    const u64* __restrict__ wo = woff + (size_t)slot * (n + 1);
+    const u64 ns = nsrc[slot];
+    for (u64 c = blockIdx.x * (u64)blockDim.x + threadIdx.x; c <= nchunks && c < chunk_cap; c += (u64)gridDim.x * blockDim.x) {
+        const u64 target = c * WALK_CHUNK;
+        u64 lo = 0, hi = ns; // invariant: wo[lo] <= target; answer in [lo, hi)
+        if (c == nchunks) {
+            chunk_first[(size_t)slot * chunk_cap + c] = (u32)(ns ? ns - 1 : 0);
+            continue;
+        }
+        while (hi - lo > 1) {
+            const u64 mid = (lo + hi) >> 1;
+            if (wo[mid] <= target) lo = mid;
+            else hi = mid;
+        }
+        chunk_first[(size_t)slot * chunk_cap + c] = (u32)lo;
+    }
+}
+
+struct WalkArgs {
+    int32_t n;
+    u32 alpha_thr;   // stop iff 32-bit draw < alpha * 2^32
+    u32 seed_lo, seed_hi;
+    int with_idx;
+    const int32_t* __restrict__ srcs;
+    const u64* __restrict__ woff;
+    const double* __restrict__ incs;
+    const u64* __restrict__ nsrc;
+    const u64* __restrict__ nwalk;
+    const u32* __restrict__ chunk_first;
+    size_t chunk_cap;
+    const int32_t* __restrict__ slot_state;
+    const u32* __restrict__ qid;   // [slots] global query index (Philox key)
+    u32 round_tag;
+    double* ppr;                   // [slots*n]
+    u64* __restrict__ hops;        // [slots]
+    u64* __restrict__ idx_hits;    // [slots]
+    // walk index (build.h): flat destinations + (offset,count) per vertex
+    const u64* __restrict__ idx_off;
+    const u64* __restrict__ idx_cnt;
+    const int32_t* __restrict__ idx_dest;
+    const u64* __restrict__ idx_used; // per-round cursor (top-k), may be null
+};
+
+// The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
+// iteration first stops with probability alpha (skipped once when NO_ZERO_HOP), then moves to a
+// uniform out-neighbour, or back to THIS walk's start when the current vertex is dangling.
+struct Walker {
+    int32_t cur, start;
+    u32 jlo, jhi; // walk index within its source (Philox counter words 0,1)
+    u32 blk;      // Philox draw-block counter (counter word 2)
+    u32 phase;    // 0: draw a new block; 1: second half of the current block
+    Philox4 rnd;
+    bool first;   // forced first hop pending (NO_ZERO_HOP)
+};
+
+template <typename OffT, bool NO_ZERO_HOP>
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<OffT> g) {
+    __shared__ long long s_rel[WALK_CHUNK + 2];
+    const int slot = blockIdx.y;
+    if (a.slot_state[slot] != 1) return;
+    const u64 W = a.nwalk[slot];
+    if (W == 0) return;
+    const u64 nchunks = (W + WALK_CHUNK - 1) / WALK_CHUNK;
+    const int32_t* __restrict__ srcs = a.srcs + (size_t)slot * a.n;
+    const u64* __restrict__ woff = a.woff + (size_t)slot * (a.n + 1);
+    const double* __restrict__ incs = a.incs + (size_t)slot * a.n;
+    const u32* __restrict__ cfirst = a.chunk_first + (size_t)slot * a.chunk_cap;
+    double* ppr = a.ppr + (size_t)slot * a.n;
+    const u32 k0 = a.seed_lo ^ (a.qid[slot] * 0x9E3779B9u), k1 = a.seed_hi ^ a.round_tag;
+    u64 my_hops = 0, my_hits = 0;
+
+    for (u64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+        const u64 w0 = chunk * WALK_CHUNK;
+        const u64 w1 = min(W, w0 + (u64)WALK_CHUNK);
+        const u32 s_lo = cfirst[chunk], s_hi = cfirst[chunk + 1];
+        const u32 cnt = s_hi - s_lo + 1; // sources touching this chunk, <= WALK_CHUNK + 1
+        __syncthreads();
+        for (u32 i = threadIdx.x; i <= cnt; i += WALK_THREADS) s_rel[i] = (long long)woff[s_lo + i] - (long long)w0;
+        __syncthreads();
+
+        u64 w = w0 + threadIdx.x;
+        bool need_init = true;
+        Walker wk;
+        double inc = 0.0;
+        while (w < w1) {
+            if (need_init) {
+                // source of walk w: last i in [0,cnt) with s_rel[i] <= w - w0
+                const long long x = (long long)(w - w0);
+                u32 lo = 0, hi = cnt;
+                while (hi - lo > 1) {
+                    const u32 mid = (lo + hi) >> 1;
+                    if (s_rel[mid] <= x) lo = mid;
+                    else hi = mid;
+                }
+                const u64 j = (u64)(x - s_rel[lo]);
+                const int32_t v = srcs[s_lo + lo];
+                inc = incs[s_lo + lo];
+                wk.cur = wk.start = v;
+                wk.jlo = (u32)j;
+                wk.jhi = (u32)(j >> 32);
+                wk.blk = 0;
+                wk.phase = 0;
+                wk.first = NO_ZERO_HOP;
+                need_init = false;
+                bool done = false;
+                int32_t dest = v;
+                if (a.with_idx) { // query.h:290-307: the first min(n_v, count) walks come from the index
+                    const u64 used = a.idx_used ? a.idx_used[(size_t)slot * a.n + v] : 0;
+                    const u64 have = a.idx_cnt[v] - used;
+                    if (j < have) {
+                        dest = a.idx_dest[a.idx_off[v] + used + j];
+                        done = true;
+                        ++my_hits;
+                    }
+                }
+                if (!done && (u32)(g.ptr[v + 1] - g.ptr[v]) == 0) done = true; // algo.h:127-129
+                if (done) {
+                    atomicAdd(&ppr[dest], inc);
+                    w += WALK_THREADS;
+                    need_init = true;
+                    continue;
+                }
+            }
+            // Philox counter = (walk index lo, hi, draw block, source); one block feeds two steps
+            if (wk.phase == 0) wk.rnd = philox4x32_10(wk.jlo, wk.jhi, wk.blk++, (u32)wk.start, k0, k1);
+            const u32 r_stop = wk.phase ? wk.rnd.z : wk.rnd.x;
+            const u32 r_pick = wk.phase ? wk.rnd.w : wk.rnd.y;
+            wk.phase ^= 1u;
+            if (!wk.first && r_stop < a.alpha_thr) { // algo.h:131-133
+                atomicAdd(&ppr[wk.cur], inc);
+                w += WALK_THREADS;
+                need_init = true;
+                continue;
+            }
+            wk.first = false;
+            const OffT b = g.ptr[wk.cur];
+            const u32 d = (u32)(g.ptr[wk.cur + 1] - b);
+            if (d) {
+                wk.cur = __ldg(&g.col[b + (OffT)__umulhi(r_pick, d)]); // algo.h:135-136
+                ++my_hops;
+            } else {
+                wk.cur = wk.start; // algo.h:138-140
+            }
+        }
+    }
+    my_hops = warp_sum(my_hops);
+    my_hits = warp_sum(my_hits);
+    if (lane_id() == 0) {
+        if (my_hops) atomicAdd(&a.hops[slot], my_hops);
+        if (my_hits) atomicAdd(&a.idx_hits[slot], my_hits);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Bulk walk destinations from explicit (start, count) segments: test hook (random_walk x count),
+// Monte-Carlo baseline (omega walks from s, query.h:25-31) and index build (build.h:344-354).
+// Walk `j` of a segment starting at global position `base` writes dest[base + j] and/or counts it.
+// ---------------------------------------------------------------------------------------------
+struct BulkArgs {
+    u32 alpha_thr, seed_lo, seed_hi;
+    u32 key_tag;                       // distinguishes index build / MC / test streams
+    const u64* __restrict__ seg_off;   // [nseg+1] exclusive prefix of counts, relative to v_begin's offset
+    int32_t v_begin;                   // segment i walks from vertex v_begin + i (or from `single` if >= 0)
+    int32_t single;
+    u64 nseg;
+    u64 total;
+    int32_t* __restrict__ dest;        // may be null
+    u64* __restrict__ counts;          // [n] destination histogram, may be null
+    u64* __restrict__ hops;            // [1]
+};
+
+template <typename OffT, bool NO_ZERO_HOP>
+__global__ void __launch_bounds__(WALK_THREADS) bulk_walk_kernel(BulkArgs a, CsrView<OffT> g) {
+    const u32 k0 = a.seed_lo ^ (a.key_tag * 0x9E3779B9u), k1 = a.seed_hi ^ 0x5bd1e995u;
+    u64 my_hops = 0;
+    for (u64 w = blockIdx.x * (u64)WALK_THREADS + threadIdx.x; w < a.total; w += (u64)gridDim.x * WALK_THREADS) {
+        int32_t start;
+        u64 j;
+        if (a.single >= 0) {
+            start = a.single;
+            j = w;
+        } else { // segment of w: last i with seg_off[i] <= w
+            u64 lo = 0, hi = a.nseg;
+            while (hi - lo > 1) {
+                const u64 mid = (lo + hi) >> 1;
+                if (a.seg_off[mid] <= w) lo = mid;
+                else hi = mid;
+            }
+            start = a.v_begin + (int32_t)lo;
+            j = w - a.seg_off[lo];
+        }
+        int32_t cur = start;
+        OffT b = g.ptr[cur];
+        u32 d = (u32)(g.ptr[cur + 1] - b);
+        if (d != 0) {
+            bool first = NO_ZERO_HOP;
+            u32 blk = 0;
+            for (;;) {
+                const Philox4 rnd = philox4x32_10((u32)j, (u32)(j >> 32), blk++, (u32)start, k0, k1);
+                // two steps per Philox call
+                if (!first && rnd.x < a.alpha_thr) break;
+                first = false;
+                if (d) { cur = __ldg(&g.col[b + (OffT)__umulhi(rnd.y, d)]); ++my_hops; }
+                else cur = start;
+                b = g.ptr[cur];
+                d = (u32)(g.ptr[cur + 1] - b);
+                if (rnd.z < a.alpha_thr) break;
+                if (d) { cur = __ldg(&g.col[b + (OffT)__umulhi(rnd.w, d)]); ++my_hops; }
+                else cur = start;
+                b = g.ptr[cur];
+                d = (u32)(g.ptr[cur + 1] - b);
+            }
+        }
+        if (a.dest) a.dest[w] = cur;
+        if (a.counts) atomicAdd(&a.counts[cur], 1ull);
+    }
+    my_hops = warp_sum(my_hops);
+    if (lane_id() == 0 && my_hops) atomicAdd(a.hops, my_hops);
+}
+
+// ppr[v] = counts[v] * 1.0 / omega   (query.h:35-38)
+__global__ void counts_to_ppr_kernel(int32_t n, const u64* __restrict__ counts, double omega, double* __restrict__ ppr) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x)
+        ppr[v] = counts[v] ? (double)counts[v] * 1.0 / omega : 0.0;
+}
+
+} // namespace fora
