@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -37,9 +38,15 @@ template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t cap = 0;
+    bool owned = true;
+    void alias(T* ptr, size_t count) { // view into the hot arena
+        if (p && owned) cudaFree(p);
+        p = ptr; cap = count; owned = false;
+    }
     cudaError_t ensure(size_t count) {
         if (count <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
+        owned = true;
         p = nullptr;
         cap = 0;
         cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
@@ -47,9 +54,10 @@ struct DevBuf {
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p && owned) cudaFree(p);
         p = nullptr;
         cap = 0;
+        owned = true;
     }
 };
 
@@ -65,11 +73,22 @@ struct fora_ctx {
     bool params_set = false;
     int slots = 4;
     int alloc_slots = 0;
-    // dense per-slot state
+    // hot arena: [residue | deg | row offsets (u32) | reserve] in ONE allocation so that an L2 access-policy
+    // window can pin the arrays every edge / hop touches at random (B200: 126 MB L2)
+    DevBuf<unsigned char> arena;
+    int32_t* hot_deg = nullptr;
+    u32* hot_ptr32 = nullptr;
+    size_t win_push_off = 0, win_push_bytes = 0, win_walk_off = 0, win_walk_bytes = 0;
+    size_t l2_persist_max = 0, l2_window_max = 0;
+    bool l2_policy = true;
+    // dense per-slot state (views into the arena)
     DevBuf<double> reserve, residue;
     DevBuf<u64> front0, front1;
     DevBuf<double> inc;
-    DevBuf<u32> hub;
+    DevBuf<u32> eoff;
+    DevBuf<u64> block_sum;
+    DevBuf<u64> trace; // FORA_PUSH_TRACE=1: per-level trace of the last push launch
+    bool trace_on = false;
     DevBuf<PushCtl> ctl;
     DevBuf<SlotMeta> meta;
     SlotMeta* h_meta = nullptr; // pinned
@@ -152,6 +171,10 @@ extern "C" int fora_ctx_create(int device, uint64_t seed, fora_ctx** out) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
+    ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+    ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+    ctx->l2_policy = getenv("FORA_NO_L2_POLICY") == nullptr && ctx->l2_persist_max > 0;
+    if (ctx->l2_policy) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
     if (!prop.cooperativeLaunch) {
         g_create_error = "device lacks cooperative launch";
         delete ctx;
@@ -182,8 +205,8 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     free_graph(ctx->g);
-    ctx->reserve.release(); ctx->residue.release(); ctx->front0.release(); ctx->front1.release();
-    ctx->inc.release(); ctx->hub.release(); ctx->ctl.release(); ctx->meta.release();
+    ctx->reserve.release(); ctx->residue.release(); ctx->arena.release(); ctx->front0.release(); ctx->front1.release();
+    ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
     ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
@@ -318,12 +341,37 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
     if (ctx->alloc_slots < S) {
         const size_t fcap = n * S;
         if (fcap >= 0xffffffffull) return ctx->fail(FORA_EINVAL, "slots*n must stay below 2^32");
-        CK(ctx->reserve.ensure(n * S));
-        CK(ctx->residue.ensure(n * S));
+        {
+            auto pad = [](size_t b) { return (b + 255) & ~(size_t)255; };
+            const size_t b_res = pad(n * S * sizeof(double)), b_deg = pad(n * sizeof(int32_t)), b_ptr = pad((n + 1) * sizeof(u32));
+            ctx->reserve.release(); ctx->residue.release();
+            CK(ctx->arena.ensure(2 * b_res + b_deg + b_ptr));
+            unsigned char* base = ctx->arena.p;
+            ctx->residue.alias((double*)base, n * S);
+            ctx->hot_deg = (int32_t*)(base + b_res);
+            ctx->hot_ptr32 = (u32*)(base + b_res + b_deg);
+            ctx->reserve.alias((double*)(base + b_res + b_deg + b_ptr), n * S);
+            CK(cudaMemcpyAsync(ctx->hot_deg, g.deg, n * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (g.off32) CK(cudaMemcpyAsync(ctx->hot_ptr32, g.out_ptr32, (n + 1) * sizeof(u32), cudaMemcpyDeviceToDevice, ctx->stream));
+            // push touches residue + deg per edge, walks touch row offsets per hop and ppr per walk.  Pin
+            // them when they fit the persisting carve-out (one slot at LJ scale); with more slots only the
+            // slot-independent arrays (deg, row offsets) are pinned.
+            ctx->win_push_off = 0;
+            ctx->win_push_bytes = b_res + b_deg;
+            ctx->win_walk_off = b_res + b_deg;
+            ctx->win_walk_bytes = b_ptr + b_res;
+            if (ctx->win_push_bytes > ctx->l2_persist_max) { ctx->win_push_off = b_res; ctx->win_push_bytes = b_deg + b_ptr; }
+            if (ctx->win_walk_bytes > ctx->l2_persist_max) { ctx->win_walk_off = b_res; ctx->win_walk_bytes = b_deg + b_ptr; }
+            if (ctx->win_push_bytes > ctx->l2_persist_max) ctx->win_push_bytes = 0; // huge graphs: leave the L2 alone
+            if (ctx->win_walk_bytes > ctx->l2_persist_max) ctx->win_walk_bytes = 0;
+        }
         CK(ctx->front0.ensure(fcap));
         CK(ctx->front1.ensure(fcap));
         CK(ctx->inc.ensure(fcap));
-        CK(ctx->hub.ensure(fcap));
+        CK(ctx->eoff.ensure(fcap + 1));
+        CK(ctx->block_sum.ensure(MAX_PUSH_CTAS));
+        ctx->trace_on = getenv("FORA_PUSH_TRACE") != nullptr;
+        if (ctx->trace_on) { CK(ctx->trace.ensure(4 * 4096)); CK(cudaMemset(ctx->trace.p, 0, sizeof(u64) * 4 * 4096)); }
         CK(ctx->ctl.ensure(1));
         CK(ctx->meta.ensure(1));
         ctx->red_blocks = std::max(1, std::min<int>(ctx->num_sms * 4, (int)((n + 4095) / 4096)));
@@ -339,10 +387,15 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         ctx->chunk_cap = 0;
         // occupancy-sized cooperative grid
         int per_sm = 0;
-        if (g.off32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<u32>, PUSH_THREADS, 0));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<int64_t>, PUSH_THREADS, 0));
+        if (g.off32) {
+            CK(cudaFuncSetAttribute(push_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<u32>)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<u32>, PUSH_THREADS, sizeof(PushSmem<u32>)));
+        } else {
+            CK(cudaFuncSetAttribute(push_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<int64_t>)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<int64_t>, PUSH_THREADS, sizeof(PushSmem<int64_t>)));
+        }
         if (per_sm < 1) return ctx->fail(FORA_ECUDA, "push kernel does not fit on an SM");
-        ctx->push_grid = per_sm * ctx->num_sms;
+        ctx->push_grid = std::min(per_sm * ctx->num_sms, MAX_PUSH_CTAS);
     }
     // walks per slot <= omega*rsum + #sources <= omega + n
     const size_t need = (size_t)((omega_max + (double)n) / WALK_CHUNK) + 4;
@@ -350,6 +403,27 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         CK(ctx->chunk_first.ensure(need * S));
         ctx->chunk_cap = need;
     }
+    return FORA_OK;
+}
+
+// Pin [arena+off, +bytes) in L2 for the kernels launched next on the work stream (bytes == 0 clears).
+static int set_l2_window(fora_ctx* ctx, size_t off, size_t bytes) {
+    if (!ctx->l2_policy) return FORA_OK;
+    cudaStreamAttrValue av;
+    memset(&av, 0, sizeof av);
+    if (bytes) {
+        const size_t wb = std::min(bytes, ctx->l2_window_max);
+        av.accessPolicyWindow.base_ptr = ctx->arena.p + off;
+        av.accessPolicyWindow.num_bytes = wb;
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ctx->l2_persist_max / (double)wb);
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    } else {
+        av.accessPolicyWindow.num_bytes = 0;
+        av.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        av.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+    }
+    CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &av));
     return FORA_OK;
 }
 
@@ -371,11 +445,12 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     a.alpha = ctx->p.alpha;
     a.reserve = ctx->reserve.p;
     a.residue = ctx->residue.p;
-    a.deg = ctx->g.deg;
+    a.deg = ctx->hot_deg;
     a.front0 = ctx->front0.p;
     a.front1 = ctx->front1.p;
     a.inc = ctx->inc.p;
-    a.hub = ctx->hub.p;
+    a.eoff = ctx->eoff.p;
+    a.block_sum = ctx->block_sum.p;
     a.ctl = ctx->ctl.p;
     a.rmax = m->rmax;
     a.source = m->source;
@@ -386,6 +461,8 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     a.front_cap = (u32)ctx->front0.cap;
     a.max_levels = 1u << 20;
     a.level_base = ctx->level_base;
+    a.trace = ctx->trace_on ? ctx->trace.p : nullptr;
+    a.trace_cap = ctx->trace_on ? 4096 : 0;
     return a;
 }
 
@@ -393,14 +470,16 @@ static PushArgs make_push_args(fora_ctx* ctx) {
 static int launch_push(fora_ctx* ctx) {
     PushArgs a = make_push_args(ctx);
     ctx->level_base += (1u << 20);
+    int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
+    if (wrc) return wrc;
     if (ctx->g.off32) {
-        CsrView<u32> v{ctx->g.out_ptr32, ctx->g.out_col};
+        CsrView<u32> v{ctx->hot_ptr32, ctx->g.out_col};
         void* args[] = {&a, &v};
-        CK(cudaLaunchCooperativeKernel((void*)push_kernel<u32>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, 0, ctx->stream));
+        CK(cudaLaunchCooperativeKernel((void*)push_kernel<u32>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, sizeof(PushSmem<u32>), ctx->stream));
     } else {
         CsrView<int64_t> v{ctx->g.out_ptr64, ctx->g.out_col};
         void* args[] = {&a, &v};
-        CK(cudaLaunchCooperativeKernel((void*)push_kernel<int64_t>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, 0, ctx->stream));
+        CK(cudaLaunchCooperativeKernel((void*)push_kernel<int64_t>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, sizeof(PushSmem<int64_t>), ctx->stream));
     }
     ctx->launches++;
     return FORA_OK;
@@ -432,7 +511,7 @@ static int init_wave(fora_ctx* ctx, int cnt, int seed_source, const int32_t* d_s
     CK(cudaMemsetAsync(ctx->reserve.p, 0, sizeof(double) * n * cnt, ctx->stream));
     CK(cudaMemsetAsync(ctx->residue.p, 0, sizeof(double) * n * cnt, ctx->stream));
     CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
-    push_init_kernel<<<1, MAX_SLOTS, 0, ctx->stream>>>(ctx->g.n, ctx->slots, ctx->meta.p->source, ctx->g.deg, ctx->reserve.p,
+    push_init_kernel<<<1, MAX_SLOTS, 0, ctx->stream>>>(ctx->g.n, ctx->slots, ctx->meta.p->source, ctx->hot_deg, ctx->reserve.p,
                                                       ctx->residue.p, ctx->front0.p, ctx->ctl.p, seed_source, ctx->meta.p->state);
     CKL();
     return FORA_OK;
@@ -444,7 +523,7 @@ static int push_round_active(fora_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->meta.p->active, ctx->h_meta->active, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
     const int gx = std::max(1, std::min(ctx->num_sms * 8, (ctx->g.n + 255) / 256));
-    push_seed_kernel<<<dim3(gx, ctx->slots), 256, 0, ctx->stream>>>(ctx->g.n, ctx->g.deg, ctx->residue.p, ctx->meta.p->rmax,
+    push_seed_kernel<<<dim3(gx, ctx->slots), 256, 0, ctx->stream>>>(ctx->g.n, ctx->hot_deg, ctx->residue.p, ctx->meta.p->rmax,
                                                                    ctx->meta.p->active, ctx->front0.p, ctx->ctl.p);
     CKL();
     int rc = launch_push(ctx);
@@ -540,8 +619,12 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.round_tag = round_tag; wa.ppr = ppr; wa.hops = m->hops; wa.idx_hits = m->idx_hits;
     wa.idx_off = ctx->idx_off.p; wa.idx_cnt = ctx->idx_cnt.p; wa.idx_dest = ctx->idx_dest.p; wa.idx_used = idx_used;
     const int wgx = ctx->num_sms * 8;
+    if (ppr == ctx->reserve.p) {
+        int wrc = set_l2_window(ctx, ctx->win_walk_off, ctx->win_walk_bytes);
+        if (wrc) return wrc;
+    }
     if (g.off32) {
-        CsrView<u32> v{g.out_ptr32, g.out_col};
+        CsrView<u32> v{ctx->hot_ptr32, g.out_col};
         if (no_zero_hop) walk_kernel<u32, true><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
         else walk_kernel<u32, false><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
     } else {
@@ -920,4 +1003,14 @@ extern "C" int fora_reverse_push(fora_ctx* ctx, int32_t, double, double*, double
 extern "C" int fora_topk_batch(fora_ctx* ctx, int, const int32_t*, int32_t, uint32_t, int32_t*, double*, int32_t*,
                                fora_query_stat*, fora_batch_timing*) {
     return ctx ? ctx->fail(FORA_EINVAL, "fora_topk_batch: not implemented in this build") : FORA_EINVAL;
+}
+
+// development aid: copy the per-level trace of the last push launch (FORA_PUSH_TRACE=1); returns levels
+extern "C" int fora_debug_push_trace(fora_ctx* ctx, uint64_t* out, int cap_levels) {
+    if (!ctx || !ctx->trace_on) return 0;
+    PushCtl h;
+    cudaMemcpy(&h, ctx->ctl.p, sizeof h, cudaMemcpyDeviceToHost);
+    const int lv = std::min<int>({(int)h.levels_run, cap_levels, 4096});
+    cudaMemcpy(out, ctx->trace.p, sizeof(u64) * 4 * lv, cudaMemcpyDeviceToHost);
+    return lv;
 }

@@ -11,10 +11,10 @@
 //                     atomic returns, so no per-vertex flag array and no per-level scan)
 //
 // One persistent cooperative kernel runs every level of every query slot of a batch; the
-// frontier test and termination live on the device.  Work is edge-balanced inside a warp
-// (32 frontier entries -> their concatenated edge ranges are walked 32 edges at a time, so
-// column reads are coalesced and a degree-1000 vertex costs its warp 32 iterations, not 1000);
-// vertices above HUB_DEG are split over the whole grid.
+// frontier test and termination live on the device.  Work is edge-balanced across the grid: the
+// edges of a level are laid on one line (exclusive scan of the frontier's out-degrees) and cut
+// into equal slices, one per CTA, so a power-law hub is simply split across CTAs and no warp
+// ever waits for a straggler; column reads are coalesced.
 #pragma once
 #include <cooperative_groups.h>
 
@@ -25,15 +25,18 @@ namespace cg = cooperative_groups;
 
 constexpr int PUSH_THREADS = 512;
 constexpr int PUSH_WARPS = PUSH_THREADS / WARP;
-constexpr int HUB_DEG = 8192;
 constexpr int MAX_SLOTS = 64;
+constexpr int MAX_PUSH_CTAS = 512;
+constexpr u32 MIN_PIECE = 1024;  // smallest edge range worth giving to a CTA
+constexpr int PUSH_UA = 4;       // frontier entries per thread per phase-A batch
+constexpr int PUSH_BATCH = 1024; // frontier entries staged in shared memory per phase-B batch
+constexpr int PUSH_UB = 4;       // edges in flight per lane in phase B
+constexpr int PUSH_WQ = 256;     // per-warp queue of crossing vertices
 
 struct PushCtl {
     u32 fcount[3];   // frontier sizes, rotated by level % 3
-    u32 tile_ctr[3]; // dynamic tile hand-out, rotated likewise
-    u32 hub_count[2];
     u32 levels_run;
-    u32 overflow;
+    u32 pad[4];
 };
 
 struct PushArgs {
@@ -43,10 +46,11 @@ struct PushArgs {
     double* reserve;  // [slots*n]   (mutated across levels: no __restrict__, read with __ldcg)
     double* residue;  // [slots*n]
     const int32_t* __restrict__ deg;
-    u64* front0;                   // (slot<<32 | v)
+    u64* front0;      // (slot<<32 | v)
     u64* front1;
     double* inc;      // per frontier entry: ((1-alpha)*r)/d, or (1-alpha)*r when dangling
-    u32* hub;         // frontier indices of hubs of this level
+    u32* eoff;        // per frontier entry: edge offset inside its CTA chunk
+    u64* block_sum;   // [gridDim.x] edges per CTA chunk of the current level
     PushCtl* ctl;
     const double* __restrict__ rmax;     // [slots]
     const int32_t* __restrict__ source;  // [slots]
@@ -57,179 +61,323 @@ struct PushArgs {
     u32 front_cap;
     u32 max_levels;
     u32 level_base;                      // distinguishes levels of successive launches in lastlvl
+    u64* trace;                          // optional [4*trace_cap]: per level {t0 ns, nf, E, t after phase A}
+    u32 trace_cap;
 };
 
-// One scatter: residue[slot*n+u] += inc, and detect the threshold crossing (see header).
-// Called by all 32 lanes (ok = lane has an edge).
-__device__ __forceinline__ void push_scatter(const PushArgs& a, bool ok, int slot, int32_t u, double inc, double rmax,
-                                             u64* nxt, u32* nxt_count) {
-    bool cross = false;
-    if (ok) {
-        const size_t g = (size_t)slot * a.n + u;
-        const double old = atomicAdd(&a.residue[g], inc);
-        const double nw = old + inc;
-        const int32_t du = __ldg(&a.deg[u]);
-        const double thr = rmax * (double)du;
-        cross = du ? (old < thr && nw >= thr) : (old == 0.0);
+// dynamic shared memory of the push kernel (~70 KB, two CTAs per SM)
+template <typename OffT>
+struct PushSmem {
+    u64 base[MAX_PUSH_CTAS + 1]; // exclusive prefix of block_sum
+    u64 G[PUSH_BATCH + 1];       // global edge offset of each entry of the current batch
+    double inc[PUSH_BATCH];
+    OffT beg[PUSH_BATCH];
+    int slot[PUSH_BATCH];        // slot, or ~slot when the entry is dangling
+    u64 wqueue[PUSH_WARPS][PUSH_WQ]; // crossing vertices, one private queue per warp (no shared atomics)
+    u64 warp_tot[PUSH_WARPS];
+    double rmax[MAX_SLOTS];
+    int32_t source[MAX_SLOTS];
+    u32 cnt_edges[MAX_SLOTS], cnt_verts[MAX_SLOTS];
+    u32 i0;
+};
+
+// block-wide inclusive scan of one u64 per thread; returns the inclusive value, *total = block sum
+template <typename OffT>
+__device__ __forceinline__ u64 block_incl_scan(PushSmem<OffT>& sm, u64 v, u64* total) {
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    u64 incl = warp_incl_scan64(v);
+    if (lane == 31) sm.warp_tot[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        u64 t = lane < PUSH_WARPS ? sm.warp_tot[lane] : 0;
+        const u64 ti = warp_incl_scan64(t);
+        if (lane < PUSH_WARPS) sm.warp_tot[lane] = ti; // inclusive over warps
     }
-    warp_append<u64>(cross, ((u64)slot << 32) | (u32)u, nxt, nxt_count);
+    __syncthreads();
+    *total = sm.warp_tot[PUSH_WARPS - 1];
+    if (w > 0) incl += sm.warp_tot[w - 1];
+    __syncthreads();
+    return incl;
+}
+
+// ---- phase A: CTA `rank` of `count` takes a contiguous chunk of the frontier: snapshot + zero the
+// residues, credit the reserves, and lay the chunk's edges out on a line (eoff = exclusive scan
+// of the out-degrees; a dangling vertex owns one pseudo-edge back to its slot's source).
+// Every thread owns PUSH_UA consecutive entries and issues all their loads before using any.
+template <typename OffT>
+__device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& sm, const u64* cur, u32 nf, u32 level,
+                                             u32 rank, u32 count) {
+    const int lane = lane_id();
+    const u32 cs = (nf + count - 1) / count;
+    const u32 lo_i = min(nf, rank * cs), hi_i = min(nf, lo_i + cs);
+    u64 carry = 0;
+    for (u32 b0 = lo_i; b0 < hi_i; b0 += PUSH_THREADS * PUSH_UA) {
+        const u32 i0 = b0 + threadIdx.x * PUSH_UA;
+        u64 e[PUSH_UA];
+        double r[PUSH_UA], rs[PUSH_UA];
+        u32 d[PUSH_UA];
+#pragma unroll
+        for (int k = 0; k < PUSH_UA; ++k) e[k] = (i0 + k < hi_i) ? __ldcs(&cur[i0 + k]) : ~0ull;
+#pragma unroll
+        for (int k = 0; k < PUSH_UA; ++k) {
+            r[k] = rs[k] = 0.0;
+            d[k] = 0;
+            if (e[k] != ~0ull) {
+                const size_t gi = (size_t)(e[k] >> 32) * a.n + (u32)e[k];
+                r[k] = __ldcg(&a.residue[gi]);
+                rs[k] = __ldcg(&a.reserve[gi]);
+                d[k] = (u32)__ldg(&a.deg[(u32)e[k]]);
+            }
+        }
+        u32 esum = 0, vcnt = 0, dsum = 0;
+        int slot_first = -1;
+        bool same = true;
+#pragma unroll
+        for (int k = 0; k < PUSH_UA; ++k) {
+            if (e[k] == ~0ull) continue;
+            const int slot = (int)(e[k] >> 32);
+            const size_t gi = (size_t)slot * a.n + (u32)e[k];
+            a.residue[gi] = 0.0;
+            a.reserve[gi] = rs[k] + r[k] * a.alpha;
+            a.inc[i0 + k] = d[k] ? ((1.0 - a.alpha) * r[k]) / (double)d[k] : r[k] * (1.0 - a.alpha);
+            a.eoff[i0 + k] = esum; // thread-local exclusive offset, completed below
+            esum += d[k] ? d[k] : 1u;
+            dsum += d[k];
+            ++vcnt;
+            if (slot_first < 0) slot_first = slot;
+            else same = same && slot == slot_first;
+        }
+        // per-slot work counters (cost model of --balanced, roofline accounting): shared memory first
+        const int slot0 = __shfl_sync(FULL, slot_first, 0);
+        if (__all_sync(FULL, same && (slot_first == slot0 || slot_first < 0))) {
+            const u32 ds = warp_sum(dsum), vc = warp_sum(vcnt);
+            if (lane == 0 && slot0 >= 0) {
+                atomicAdd(&sm.cnt_edges[slot0], ds);
+                atomicAdd(&sm.cnt_verts[slot0], vc);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < PUSH_UA; ++k)
+                if (e[k] != ~0ull) {
+                    atomicAdd(&sm.cnt_edges[(int)(e[k] >> 32)], d[k]);
+                    atomicAdd(&sm.cnt_verts[(int)(e[k] >> 32)], 1u);
+                }
+        }
+        u64 total;
+        const u64 incl = block_incl_scan(sm, (u64)esum, &total);
+        const u32 tbase = (u32)(carry + incl - esum);
+#pragma unroll
+        for (int k = 0; k < PUSH_UA; ++k)
+            if (e[k] != ~0ull) a.eoff[i0 + k] += tbase;
+        carry += total;
+    }
+    if (threadIdx.x == 0) a.block_sum[rank] = carry;
+    // flush the per-slot counters of this CTA (block_incl_scan's barriers ordered the shared atomics)
+    if (lo_i < hi_i && threadIdx.x < (u32)a.slots) {
+        const int sl = threadIdx.x;
+        const u32 v = sm.cnt_verts[sl];
+        if (v) {
+            const int lvl = (int)(a.level_base + level + 1);
+            atomicAdd(&a.edges[sl], (u64)sm.cnt_edges[sl]);
+            atomicAdd(&a.vertices[sl], (u64)v);
+            if (a.lastlvl[sl] < lvl && atomicMax(&a.lastlvl[sl], lvl) < lvl) atomicAdd(&a.levels[sl], 1ull);
+            sm.cnt_edges[sl] = 0;
+            sm.cnt_verts[sl] = 0;
+        }
+    }
+}
+
+// ---- phase B: the level's edges form one line of length E (chunk bases + eoff); CTA `rank` owns
+// the slice [rank*P, (rank+1)*P): perfectly edge-balanced whatever the degree distribution, a
+// hub is simply cut across CTAs.  Entries are staged PUSH_BATCH at a time in shared memory; inside
+// a batch the warps run independently (no CTA barrier in the edge loop): a warp step covers
+// 32*PUSH_UB consecutive edges, every lane keeps PUSH_UB scatters in flight, owners are found by
+// binary search in shared memory, column reads are coalesced and streamed past the L2-resident
+// residue vector, and crossing vertices collect in a private per-warp queue that is appended to
+// the next frontier with one global atomic per flush.
+template <typename OffT>
+__device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<OffT>& g, PushSmem<OffT>& sm, const u64* cur,
+                                             u32 nf, u32 level, u32 rank, u32 count, u64* nxt, u32* nxt_count) {
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const u32 cs = (nf + count - 1) / count;
+    for (u32 b = threadIdx.x; b < count; b += PUSH_THREADS) sm.base[b] = __ldcg(&a.block_sum[b]); // one parallel round
+    __syncthreads();
+    if (w == 0) {
+        u64 carry = 0;
+        for (u32 b0 = 0; b0 < count; b0 += WARP) {
+            const u32 b = b0 + lane;
+            const u64 v = b < count ? sm.base[b] : 0;
+            const u64 incl = warp_incl_scan64(v);
+            if (b < count) sm.base[b] = carry + incl - v;
+            carry += __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == 0) sm.base[count] = carry;
+    }
+    __syncthreads();
+    const u64 E = sm.base[count];
+    if (a.trace && rank == 0 && threadIdx.x == 0 && level < a.trace_cap) a.trace[4 * level + 2] = E;
+    if (E == 0) return;
+    u64 P = (E + count - 1) / count;
+    if (P < MIN_PIECE) P = MIN_PIECE;
+    const u64 lo = (u64)rank * P;
+    if (lo >= E) return;
+    const u64 hi = min(E, lo + P);
+    // first entry of the slice: largest i with G(i) <= lo, G(i) = base[i / cs] + eoff[i]
+    if (w == 0) {
+        u32 c = 0; // largest chunk with base[c] <= lo (only trailing chunks are empty, and they sit at E)
+        {
+            u32 l = 0, h = count;
+            while (h - l > 1) {
+                const u32 mid = (l + h) >> 1;
+                if (sm.base[mid] <= lo) l = mid;
+                else h = mid;
+            }
+            c = l;
+        }
+        const u64 target = lo - sm.base[c];
+        u32 l = min(nf, c * cs), h = min(nf, l + cs); // answer in [l, h), eoff[l] == 0 <= target
+        while (h - l > 1) {                            // 32-ary search
+            const u32 span = h - l;
+            const u32 step = (span + WARP - 1) / WARP;
+            const u32 pos = l + lane * step;
+            const bool le = pos < h && (u64)__ldcg(&a.eoff[pos]) <= target;
+            const u32 m = __ballot_sync(FULL, le);
+            const int last = 31 - __clz(m); // lane 0 always satisfies
+            const u32 nl = l + last * step;
+            h = min(h, nl + step);
+            l = nl;
+        }
+        if (lane == 0) sm.i0 = l;
+    }
+    __syncthreads();
+    u32 i_cur = sm.i0;
+    u32 wq = 0; // entries in this warp's queue (warp-uniform register)
+    u64* myq = sm.wqueue[w];
+    for (;;) {
+        const u32 cnt = min((u32)PUSH_BATCH, nf - i_cur);
+        for (u32 t = threadIdx.x; t <= cnt; t += PUSH_THREADS) {
+            const u32 i = i_cur + t;
+            if (t < cnt) {
+                const u64 e = __ldcs(&cur[i]);
+                const int slot = (int)(e >> 32);
+                const int32_t v = (int32_t)(u32)e;
+                const OffT beg = g.ptr[v];
+                const bool dang = g.ptr[v + 1] == beg;
+                sm.G[t] = sm.base[i / cs] + __ldcg(&a.eoff[i]);
+                sm.beg[t] = beg;
+                sm.inc[t] = __ldcg(&a.inc[i]);
+                sm.slot[t] = dang ? ~slot : slot;
+            } else {
+                sm.G[cnt] = i < nf ? sm.base[i / cs] + __ldcg(&a.eoff[i]) : E;
+            }
+        }
+        __syncthreads();
+        const u64 x_lo = max(lo, sm.G[0]), x_hi = min(hi, sm.G[cnt]);
+        // warp w takes steps w, w + PUSH_WARPS, ... of 32*PUSH_UB consecutive edges
+        for (u64 xb = x_lo + (u64)w * (WARP * PUSH_UB); xb < x_hi; xb += (u64)PUSH_WARPS * WARP * PUSH_UB) {
+            if (wq > PUSH_WQ - WARP * PUSH_UB) { // make room: one global atomic per flush
+                u32 base = 0;
+                if (lane == 0) base = atomicAdd(nxt_count, wq);
+                base = __shfl_sync(FULL, base, 0);
+                for (u32 t = lane; t < wq; t += WARP) nxt[base + t] = myq[t];
+                __syncwarp();
+                wq = 0;
+            }
+            int slot[PUSH_UB];
+            int32_t u[PUSH_UB];
+            double inc[PUSH_UB], old[PUSH_UB];
+            bool ok[PUSH_UB];
+            u32 l = 0;
+#pragma unroll
+            for (int k = 0; k < PUSH_UB; ++k) {
+                const u64 x = xb + (u64)k * WARP + lane;
+                ok[k] = x < x_hi;
+                slot[k] = 0; u[k] = 0; inc[k] = 0.0;
+                if (ok[k]) {
+                    // largest t in [l, h) with G[t] <= x; after the first edge the owner moves forward by at
+                    // most 32 entries (every entry owns >= 1 edge)
+                    u32 h = k == 0 ? cnt : min(cnt, l + WARP + 1);
+                    while (h - l > 1) {
+                        const u32 mid = (l + h) >> 1;
+                        if (sm.G[mid] <= x) l = mid;
+                        else h = mid;
+                    }
+                    const int sj = sm.slot[l];
+                    slot[k] = sj < 0 ? ~sj : sj;
+                    inc[k] = sm.inc[l];
+                    u[k] = sj < 0 ? sm.source[slot[k]] : __ldcs(&g.col[sm.beg[l] + (OffT)(x - sm.G[l])]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < PUSH_UB; ++k)
+                if (ok[k]) old[k] = atomicAdd(&a.residue[(size_t)slot[k] * a.n + u[k]], inc[k]);
+#pragma unroll
+            for (int k = 0; k < PUSH_UB; ++k) {
+                bool cross = false;
+                if (ok[k]) {
+                    const double nw = old[k] + inc[k];
+                    const int32_t du = __ldg(&a.deg[u[k]]);
+                    const double thr = sm.rmax[slot[k]] * (double)du;
+                    cross = du ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
+                }
+                const u32 m = __ballot_sync(FULL, cross);
+                if (cross) myq[wq + __popc(m & lanemask_lt())] = ((u64)slot[k] << 32) | (u32)u[k];
+                wq += __popc(m);
+            }
+        }
+        const bool more = sm.G[cnt] < hi && i_cur + cnt < nf;
+        __syncthreads();
+        if (!more) break;
+        i_cur += cnt;
+    }
+    if (wq) { // final flush of this warp's queue
+        u32 base = 0;
+        __syncwarp();
+        if (lane == 0) base = atomicAdd(nxt_count, wq);
+        base = __shfl_sync(FULL, base, 0);
+        for (u32 t = lane; t < wq; t += WARP) nxt[base + t] = myq[t];
+    }
 }
 
 template <typename OffT>
 __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrView<OffT> g) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ u32 s_excl[PUSH_WARPS][WARP];
-    __shared__ OffT s_beg[PUSH_WARPS][WARP];
-    __shared__ double s_inc[PUSH_WARPS][WARP];
-    __shared__ int s_slot[PUSH_WARPS][WARP]; // slot, or ~slot when the entry is dangling
-    __shared__ double s_rmax[MAX_SLOTS];
-    __shared__ int32_t s_source[MAX_SLOTS];
-
-    const int lane = lane_id();
-    const int wib = threadIdx.x >> 5;
-    const u32 gtid = blockIdx.x * blockDim.x + threadIdx.x;
-    const u32 gsize = gridDim.x * blockDim.x;
-    const u32 gwarp = gtid >> 5;
+    extern __shared__ __align__(16) unsigned char push_smem_raw[];
+    PushSmem<OffT>& sm = *reinterpret_cast<PushSmem<OffT>*>(push_smem_raw);
     PushCtl* ctl = a.ctl;
-
-    for (int i = threadIdx.x; i < a.slots; i += blockDim.x) {
-        s_rmax[i] = a.rmax[i];
-        s_source[i] = a.source[i];
+    for (int i = threadIdx.x; i < MAX_SLOTS; i += blockDim.x) {
+        sm.rmax[i] = i < a.slots ? a.rmax[i] : 0.0;
+        sm.source[i] = i < a.slots ? a.source[i] : 0;
+        sm.cnt_edges[i] = 0;
+        sm.cnt_verts[i] = 0;
     }
     __syncthreads();
 
-    u32 level = 0;
-    for (;; ++level) {
+    for (u32 level = 0;; ++level) {
         const u32 nf = *((volatile u32*)&ctl->fcount[level % 3]);
         if (nf == 0 || level >= a.max_levels) break;
         const u64* cur = (level & 1) ? a.front1 : a.front0; // written by the previous level: L2 reads only
         u64* nxt = (level & 1) ? a.front0 : a.front1;
         u32* nxt_count = &ctl->fcount[(level + 1) % 3];
-
-        // ---------------- phase A: take the residue snapshot ----------------
-        if (gtid == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
             ctl->fcount[(level + 2) % 3] = 0;
-            ctl->tile_ctr[(level + 1) % 3] = 0;
-            ctl->hub_count[(level + 1) & 1] = 0;
             ctl->levels_run = level + 1;
-        }
-        for (u32 base = gwarp * WARP; base < nf; base += (gsize >> 5) * WARP) {
-            const u32 i = base + lane;
-            int slot = -1;
-            u32 d = 0;
-            if (i < nf) {
-                const u64 e = __ldcg(&cur[i]);
-                slot = (int)(e >> 32);
-                const int32_t v = (int32_t)(u32)e;
-                const size_t gi = (size_t)slot * a.n + v;
-                const double r = __ldcg(&a.residue[gi]);
-                a.residue[gi] = 0.0;
-                a.reserve[gi] = __ldcg(&a.reserve[gi]) + r * a.alpha;
-                d = (u32)__ldg(&a.deg[v]);
-                a.inc[i] = d ? ((1.0 - a.alpha) * r) / (double)d : r * (1.0 - a.alpha);
-            }
-            // per-slot work counters (cost model of --balanced, roofline accounting)
-            const int slot0 = __shfl_sync(FULL, slot, 0);
-            if (__all_sync(FULL, slot == slot0 || slot < 0)) {
-                const u32 dsum = warp_sum(d);
-                const u32 cnt = __popc(__ballot_sync(FULL, slot >= 0));
-                if (lane == 0) {
-                    atomicAdd(&a.edges[slot0], (u64)dsum);
-                    atomicAdd(&a.vertices[slot0], (u64)cnt);
-                    if (atomicMax(&a.lastlvl[slot0], (int)(a.level_base + level + 1)) < (int)(a.level_base + level + 1))
-                        atomicAdd(&a.levels[slot0], 1ull);
-                }
-            } else if (slot >= 0) {
-                atomicAdd(&a.edges[slot], (u64)d);
-                atomicAdd(&a.vertices[slot], 1ull);
-                if (atomicMax(&a.lastlvl[slot], (int)(a.level_base + level + 1)) < (int)(a.level_base + level + 1))
-                    atomicAdd(&a.levels[slot], 1ull);
+            if (a.trace && level < a.trace_cap) {
+                u64 t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                a.trace[4 * level] = t;
+                a.trace[4 * level + 1] = nf;
             }
         }
+        push_phase_a<OffT>(a, sm, cur, nf, level, blockIdx.x, gridDim.x);
         grid.sync();
-
-        // ---------------- phase B: scatter, 32 frontier entries per warp tile ----------------
-        const u32 ntiles = (nf + WARP - 1) / WARP;
-        u32* tile_ctr = &ctl->tile_ctr[level % 3];
-        u32* hub_count = &ctl->hub_count[level & 1];
-        // first tile of every warp is static (no atomic at all while the frontier is smaller than the
-        // grid: a same-address atomic per warp per level costs more than the level itself); further
-        // tiles are handed out dynamically
-        const u32 nwarps = gsize >> 5;
-        for (u32 round = 0;; ++round) {
-            u32 t = gwarp;
-            if (round > 0) {
-                if (ntiles <= nwarps) break;
-                if (lane == 0) t = nwarps + atomicAdd(tile_ctr, 1u);
-                t = __shfl_sync(FULL, t, 0);
-            }
-            if (t >= ntiles) break;
-            const u32 i = t * WARP + lane;
-            u32 d = 0;
-            if (i < nf) {
-                const u64 e = __ldcg(&cur[i]);
-                const int slot = (int)(e >> 32);
-                const int32_t v = (int32_t)(u32)e;
-                const OffT beg = g.ptr[v];
-                const u32 dreal = (u32)(g.ptr[v + 1] - beg);
-                s_beg[wib][lane] = beg;
-                s_inc[wib][lane] = __ldcg(&a.inc[i]);
-                s_slot[wib][lane] = dreal ? slot : ~slot;
-                d = dreal ? dreal : 1u;
-                if (dreal > (u32)HUB_DEG) {
-                    a.hub[atomicAdd(hub_count, 1u)] = i;
-                    d = 0;
-                }
-            }
-            const u32 incl = warp_incl_scan(d);
-            s_excl[wib][lane] = incl - d;
-            const u32 total = __shfl_sync(FULL, incl, 31);
-            __syncwarp();
-            for (u32 e0 = 0; e0 < total; e0 += WARP) {
-                const u32 ee = e0 + lane;
-                const bool ok = ee < total;
-                int slot = 0;
-                int32_t u = 0;
-                double inc = 0.0, rmax = 0.0;
-                if (ok) {
-                    // last j with excl[j] <= ee (entries of width 0 share their successor's offset)
-                    int lo = 0;
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1)
-                        if (lo + step < WARP && s_excl[wib][lo + step] <= ee) lo += step;
-                    const int sj = s_slot[wib][lo];
-                    slot = sj < 0 ? ~sj : sj;
-                    inc = s_inc[wib][lo];
-                    rmax = s_rmax[slot];
-                    u = sj < 0 ? s_source[slot] : __ldg(&g.col[s_beg[wib][lo] + (OffT)(ee - s_excl[wib][lo])]);
-                }
-                push_scatter(a, ok, slot, u, inc, rmax, nxt, nxt_count);
-            }
-            __syncwarp();
+        if (blockIdx.x == 0 && threadIdx.x == 0 && a.trace && level < a.trace_cap) {
+            u64 t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            a.trace[4 * level + 3] = t;
         }
+        push_phase_b<OffT>(a, g, sm, cur, nf, level, blockIdx.x, gridDim.x, nxt, nxt_count);
         grid.sync();
-
-        // ---------------- phase B2: hubs, edges split over the whole grid ----------------
-        const u32 nh = *((volatile u32*)hub_count);
-        if (nh > 0) {
-            for (u32 h = 0; h < nh; ++h) {
-                const u32 i = __ldcg(&a.hub[h]);
-                const u64 e = __ldcg(&cur[i]);
-                const int slot = (int)(e >> 32);
-                const int32_t v = (int32_t)(u32)e;
-                const OffT beg = g.ptr[v];
-                const u32 d = (u32)(g.ptr[v + 1] - beg);
-                const double inc = __ldcg(&a.inc[i]);
-                const double rmax = s_rmax[slot];
-                for (u32 e0 = gwarp * WARP; e0 < d; e0 += (gsize >> 5) * WARP) {
-                    const u32 ee = e0 + lane;
-                    const bool ok = ee < d;
-                    const int32_t u = ok ? __ldg(&g.col[beg + (OffT)ee]) : 0;
-                    push_scatter(a, ok, slot, u, inc, rmax, nxt, nxt_count);
-                }
-            }
-            grid.sync();
-        }
     }
 }
 
