@@ -46,7 +46,9 @@ class QueryStat(C.Structure):
 
 class BatchTiming(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("push_ms", C.c_float), ("walk_ms", C.c_float), ("plan_ms", C.c_float),
-                ("topk_ms", C.c_float), ("copy_ms", C.c_float), ("kernel_launches", C.c_uint64)]
+                ("topk_ms", C.c_float), ("copy_ms", C.c_float), ("kernel_launches", C.c_uint64),
+                ("push_kernel_ms", C.c_float), ("walk_kernel_ms", C.c_float),
+                ("push_kernel_launches", C.c_uint64), ("walk_kernel_launches", C.c_uint64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

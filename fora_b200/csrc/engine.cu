@@ -102,6 +102,8 @@ struct fora_ctx {
     DevBuf<u64> woff;
     DevBuf<double> incs;
     DevBuf<u32> chunk_first;
+    DevBuf<double> ppr;      // top-k rounds: ppr is rebuilt from reserve every round (query.h:533)
+    DevBuf<u64> idx_used;    // top-k with index: per-(slot,vertex) cursor into the index (rw_counter, query.h:575-603)
     size_t chunk_cap = 0;
     // index
     DevBuf<u64> idx_off, idx_cnt;
@@ -113,6 +115,12 @@ struct fora_ctx {
     DevBuf<int32_t> scratch32;
     DevBuf<double> scratchd;
     int push_grid = 0;
+    // per-kernel timing: event pairs recorded around the hot kernels, harvested after the next stream sync
+    std::vector<cudaEvent_t> kev_pool;
+    std::vector<std::pair<int, int> > kev_pending; // (pool index of start event, kind 0 push / 1 walk)
+    size_t kev_used = 0;
+    double push_kernel_ms = 0, walk_kernel_ms = 0;
+    u64 push_kernel_launches = 0, walk_kernel_launches = 0;
     u32 level_base = 0;
     u64 launches = 0;
     // resumable push session (fora_push_begin / fora_push_round)
@@ -140,10 +148,13 @@ struct fora_ctx {
                                              ":" + std::to_string(__LINE__));                   \
     } while (0)
 
-static const double DEFAULT_COST_WALK = 4.0e-10;   // s per online walk   (B200 calibration)
-static const double DEFAULT_COST_EDGE = 5.0e-11;   // s per pushed edge
-static const double DEFAULT_COST_VERTEX = 2.0e-10; // s per pushed vertex
-static const double DEFAULT_COST_LEVEL = 1.0e-6;   // s per frontier level (barrier latency, amortised over slots)
+// --balanced cost model, calibrated on B200 with the LiveJournal-shape graph (profiles/):
+// walks ~8.5 G/s (no-zero-hop, ~4.9 hops each); push ~28 G edges/s in the scatter phase and ~10 G
+// vertices/s in the gather phase with residue+deg pinned in L2; ~10 us of barrier latency per level.
+static const double DEFAULT_COST_WALK = 1.2e-10;   // s per online walk
+static const double DEFAULT_COST_EDGE = 3.5e-11;   // s per pushed edge
+static const double DEFAULT_COST_VERTEX = 1.0e-10; // s per pushed vertex
+static const double DEFAULT_COST_LEVEL = 1.0e-5;   // s per frontier level
 
 // =============================================================================================
 // context
@@ -208,11 +219,12 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     ctx->reserve.release(); ctx->residue.release(); ctx->arena.release(); ctx->front0.release(); ctx->front1.release();
     ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
-    ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
+    ctx->ppr.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
     ctx->counts.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->kev_pool) cudaEventDestroy(ev);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -427,6 +439,34 @@ static int set_l2_window(fora_ctx* ctx, size_t off, size_t bytes) {
     return FORA_OK;
 }
 
+
+// ---- per-kernel timing -----------------------------------------------------------------------
+static cudaEvent_t kev_get(fora_ctx* ctx) {
+    if (ctx->kev_used == ctx->kev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        ctx->kev_pool.push_back(e);
+    }
+    return ctx->kev_pool[ctx->kev_used++];
+}
+static void kev_begin(fora_ctx* ctx, int kind) {
+    ctx->kev_pending.push_back(std::make_pair((int)ctx->kev_used, kind));
+    cudaEventRecord(kev_get(ctx), ctx->stream);
+}
+static void kev_end(fora_ctx* ctx) { cudaEventRecord(kev_get(ctx), ctx->stream); }
+// call only after the stream has been synchronised
+static void kev_harvest(fora_ctx* ctx) {
+    for (auto& pr : ctx->kev_pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, ctx->kev_pool[pr.first], ctx->kev_pool[pr.first + 1]) == cudaSuccess) {
+            if (pr.second == 0) { ctx->push_kernel_ms += ms; ctx->push_kernel_launches++; }
+            else { ctx->walk_kernel_ms += ms; ctx->walk_kernel_launches++; }
+        }
+    }
+    ctx->kev_pending.clear();
+    ctx->kev_used = 0;
+}
+
 static int meta_h2d(fora_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->meta.p, ctx->h_meta, sizeof(SlotMeta), cudaMemcpyHostToDevice, ctx->stream));
     return FORA_OK;
@@ -434,6 +474,7 @@ static int meta_h2d(fora_ctx* ctx) {
 static int meta_d2h_sync(fora_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->h_meta, ctx->meta.p, sizeof(SlotMeta), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    kev_harvest(ctx);
     return FORA_OK;
 }
 
@@ -472,6 +513,7 @@ static int launch_push(fora_ctx* ctx) {
     ctx->level_base += (1u << 20);
     int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
     if (wrc) return wrc;
+    kev_begin(ctx, 0);
     if (ctx->g.off32) {
         CsrView<u32> v{ctx->hot_ptr32, ctx->g.out_col};
         void* args[] = {&a, &v};
@@ -481,6 +523,7 @@ static int launch_push(fora_ctx* ctx) {
         void* args[] = {&a, &v};
         CK(cudaLaunchCooperativeKernel((void*)push_kernel<int64_t>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, sizeof(PushSmem<int64_t>), ctx->stream));
     }
+    kev_end(ctx);
     ctx->launches++;
     return FORA_OK;
 }
@@ -623,6 +666,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
         int wrc = set_l2_window(ctx, ctx->win_walk_off, ctx->win_walk_bytes);
         if (wrc) return wrc;
     }
+    kev_begin(ctx, 1);
     if (g.off32) {
         CsrView<u32> v{ctx->hot_ptr32, g.out_col};
         if (no_zero_hop) walk_kernel<u32, true><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
@@ -632,6 +676,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
         if (no_zero_hop) walk_kernel<int64_t, true><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
         else walk_kernel<int64_t, false><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
     }
+    kev_end(ctx);
     CKL();
     return FORA_OK;
 }
@@ -639,7 +684,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
 static void fill_stat(fora_ctx* ctx, int s, double final_rmax, u64 rounds, fora_query_stat* st) {
     const SlotMeta* h = ctx->h_meta;
     memset(st, 0, sizeof *st);
-    st->rsum = h->state[s] == 1 ? h->rsum[s] : 0.0;
+    st->rsum = (h->state[s] == 1 || h->state[s] == 3) ? h->rsum[s] : 0.0;
     st->final_rmax = final_rmax;
     st->n_walks = h->nwalk[s];
     st->n_idx_hits = h->idx_hits[s];
@@ -802,6 +847,8 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
     ctx->session_source = -1;
     const u64 launches0 = ctx->launches;
     float push_ms = 0, walk_ms = 0, copy_ms = 0;
+    ctx->push_kernel_ms = ctx->walk_kernel_ms = 0;
+    ctx->push_kernel_launches = ctx->walk_kernel_launches = 0;
     CK(cudaEventRecord(ctx->ev[0], ctx->stream));
     std::vector<double> fr(S);
     std::vector<u64> rounds(S);
@@ -872,6 +919,8 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
         CK(cudaEventElapsedTime(&timing->total_ms, ctx->ev[0], ctx->ev[5]));
         timing->push_ms = push_ms; timing->walk_ms = walk_ms; timing->copy_ms = copy_ms;
         timing->kernel_launches = ctx->launches - launches0;
+        timing->push_kernel_ms = (float)ctx->push_kernel_ms; timing->walk_kernel_ms = (float)ctx->walk_kernel_ms;
+        timing->push_kernel_launches = ctx->push_kernel_launches; timing->walk_kernel_launches = ctx->walk_kernel_launches;
     }
     return FORA_OK;
 }
@@ -887,6 +936,174 @@ extern "C" int fora_query_batch_device(fora_ctx* ctx, int algo, const int32_t* d
 extern "C" void* fora_device_ppr(fora_ctx* ctx, int slot) {
     if (!ctx || slot < 0 || slot >= ctx->alloc_slots) return nullptr;
     return ctx->reserve.p + (size_t)ctx->g.n * slot;
+}
+
+
+// =============================================================================================
+// top-k queries: get_topk(), query.h:1139-1190
+// =============================================================================================
+// advance the per-source index cursor after a round: rw_counter[source] += min(n_v, remaining) (query.h:588,603)
+__global__ void idx_cursor_kernel(int32_t n, const int32_t* __restrict__ srcs, const u64* __restrict__ woff,
+                                  const u64* __restrict__ nsrc, const u64* __restrict__ idx_cnt, u64* __restrict__ idx_used,
+                                  const int32_t* __restrict__ slot_state) {
+    const int slot = blockIdx.y;
+    if (slot_state[slot] != 1) return;
+    const u64 ns = nsrc[slot];
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < ns; i += (u64)gridDim.x * blockDim.x) {
+        const int32_t v = srcs[(size_t)slot * n + i];
+        const u64 n_v = woff[(size_t)slot * (n + 1) + i + 1] - woff[(size_t)slot * (n + 1) + i];
+        u64* u = &idx_used[(size_t)slot * n + v];
+        const u64 remaining = idx_cnt[v] - *u;
+        *u += n_v < remaining ? n_v : remaining;
+    }
+}
+
+extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, uint32_t k, int32_t* nodes,
+                               double* values, int32_t* iters, fora_query_stat* stats, fora_batch_timing* timing) {
+    if (!ctx) return FORA_EINVAL;
+    if (!ctx->params_set) return ctx->fail(FORA_EINVAL, "fora_params_set has not been called");
+    if (!ctx->g.n) return ctx->fail(FORA_EINVAL, "no graph uploaded");
+    const int32_t n = ctx->g.n;
+    if (!(k > 1 && (int64_t)k < (int64_t)n - 1)) return ctx->fail(FORA_EINVAL, "k must satisfy 1 < k < n-1 (query.h:1317-1318)");
+    if (!sources || !nodes || !values || n_q < 0) return ctx->fail(FORA_EINVAL, "bad arguments");
+    if (algo == FORA_ALGO_BIPPR) return ctx->fail(FORA_EINVAL, "bippr top-k: use fora_bippr_query + fora_topk_of");
+    const fora_params keep = ctx->p;
+    int rc = FORA_OK;
+    auto restore = [&](int code) { ctx->p = keep; return code; };
+    const double min_delta = 1.0 / n;
+    if (algo == FORA_ALGO_FORA) {
+        if (!keep.opt) return ctx->fail(FORA_EINVAL, "top-k without --opt (fora_query_topk_with_bound, query.h:909) is not implemented yet");
+        // fora_query_topk_new (query.h:972-1045): pfail = 1/n^2; the largest omega is reached at delta = 1/n
+        double rm, om;
+        fora_host_setting(1, n, ctx->g.m_decl, keep.epsilon, min_delta, 1.0 / n / n, keep.alpha, keep.opt, keep.rmax_scale, &rm, &om);
+        if ((rc = require_ready(ctx, om))) return rc;
+    } else if ((rc = require_ready(ctx, keep.omega))) return rc;
+    const int S = ctx->slots;
+    const size_t nn = (size_t)n;
+    ctx->session_source = -1;
+    const u64 launches0 = ctx->launches;
+    ctx->push_kernel_ms = ctx->walk_kernel_ms = 0;
+    ctx->push_kernel_launches = ctx->walk_kernel_launches = 0;
+    CK(cudaEventRecord(ctx->ev[0], ctx->stream));
+    float topk_ms = 0;
+    SlotMeta* h = ctx->h_meta;
+    std::vector<double> fr(S);
+    std::vector<u64> rounds(S);
+    for (int32_t q0 = 0; q0 < n_q; q0 += S) {
+        const int cnt = std::min<int32_t>(S, n_q - q0);
+        for (int s = 0; s < cnt; ++s) {
+            if (sources[q0 + s] < 0 || sources[q0 + s] >= n) return restore(ctx->fail(FORA_EINVAL, "source out of range"));
+            h->source[s] = sources[q0 + s];
+            h->qid[s] = (u32)(q0 + s);
+        }
+        const double* result = ctx->reserve.p; // where each slot's final vector lives
+        std::vector<int32_t> it(cnt, 0);
+        std::vector<u64> tot_walks(cnt, 0), tot_hits(cnt, 0), tot_hops(cnt, 0);
+        if (algo == FORA_ALGO_FORA) {
+            CK(ctx->ppr.ensure(nn * S));
+            const bool use_idx = keep.with_idx && ctx->has_index;
+            if (use_idx) {
+                CK(ctx->idx_used.ensure(nn * S));
+                CK(cudaMemsetAsync(ctx->idx_used.p, 0, sizeof(u64) * nn * cnt, ctx->stream)); // rw_counter.reset_zero_values(), query.h:998
+            }
+            if ((rc = init_wave(ctx, cnt, 0, nullptr))) return restore(rc);
+            if ((rc = meta_d2h_sync(ctx))) return restore(rc);
+            std::vector<char> done(cnt, 0);
+            for (int s = 0; s < cnt; ++s) {
+                done[s] = h->state[s] != 1; // source without out-edges: ppr = {s:1} after one iteration (query.h:1003-1011)
+                if (h->state[s] == 2) it[s] = 1;
+            }
+            double delta = 1.0 / k / 10;                               // query.h:976
+            const double pfail = 1.0 / n / n;                          // query.h:977
+            CK(cudaMemcpyAsync(ctx->ppr.p, ctx->reserve.p, sizeof(double) * nn * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+            for (int round = 0; round < 64 && delta >= min_delta; ++round) {
+                bool any = false;
+                double rmax, omega;
+                fora_host_setting(1, n, ctx->g.m_decl, keep.epsilon, delta, pfail, keep.alpha, keep.opt, keep.rmax_scale, &rmax, &omega);
+                for (int s = 0; s < MAX_SLOTS; ++s) h->active[s] = 0;
+                for (int s = 0; s < cnt; ++s)
+                    if (!done[s]) { h->active[s] = 1; h->rmax[s] = rmax; any = true; it[s]++; }
+                if (!any) break;
+                if ((rc = push_round_active(ctx))) return restore(rc);
+                // finished slots keep their vector: only active slots are rebuilt and walked this round
+                for (int s = 0; s < cnt; ++s) h->state[s] = done[s] ? (h->state[s] == 1 ? 3 : h->state[s]) : 1;
+                CK(cudaMemcpyAsync(ctx->meta.p->state, h->state, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+                for (int s = 0; s < cnt; ++s)
+                    if (!done[s]) CK(cudaMemcpyAsync(ctx->ppr.p + nn * s, ctx->reserve.p + nn * s, sizeof(double) * nn, cudaMemcpyDeviceToDevice, ctx->stream));
+                ctx->p.omega = omega;
+                ctx->p.rmax = rmax;
+                // with index: alpha*r credit, (1-alpha) scaling, no-zero-hop walks (query.h:555-613); without: plain walks
+                // of ceil(r*omega) each (query.h:615-632)
+                if ((rc = walk_wave(ctx, ctx->ppr.p, 1, use_idx ? 1 : 0, use_idx ? 1 : 0, (u32)(round + 1), use_idx ? ctx->idx_used.p : nullptr))) return restore(rc);
+                if (use_idx) {
+                    idx_cursor_kernel<<<dim3(ctx->num_sms * 2, S), 256, 0, ctx->stream>>>(n, ctx->srcs.p, ctx->woff.p, ctx->meta.p->nsrc, ctx->idx_cnt.p, ctx->idx_used.p, ctx->meta.p->state);
+                    CKL();
+                }
+                if ((rc = meta_d2h_sync(ctx))) return restore(rc);
+                CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+                for (int s = 0; s < cnt; ++s) {
+                    if (done[s]) continue;
+                    tot_walks[s] += h->nwalk[s]; tot_hits[s] += h->idx_hits[s]; tot_hops[s] += h->hops[s];
+                    double kth = 0.0; // kth_ppr(), algo.h:578-590
+                    cudaError_t e = topk_device(ctx->stream, ctx->num_sms, ctx->ppr.p + nn * s, n, k, nullptr, nullptr, &ctx->launches, &kth);
+                    if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("kth select: ") + cudaGetErrorString(e)));
+                    if (kth >= (1 + keep.epsilon) * delta || delta <= min_delta) done[s] = 1; // query.h:1029
+                }
+                CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+                CK(cudaEventSynchronize(ctx->ev[7]));
+                float t;
+                CK(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
+                topk_ms += t;
+                CK(cudaMemsetAsync(ctx->meta.p->hops, 0, sizeof(u64) * MAX_SLOTS, ctx->stream));
+                CK(cudaMemsetAsync(ctx->meta.p->idx_hits, 0, sizeof(u64) * MAX_SLOTS, ctx->stream));
+                delta = std::max(min_delta, delta / 4.0); // query.h:1041
+                bool all = true;
+                for (int s = 0; s < cnt; ++s) all = all && done[s];
+                if (all) break;
+            }
+            result = ctx->ppr.p;
+            for (int s = 0; s < cnt; ++s) { fr[s] = ctx->p.rmax; rounds[s] = (u64)it[s]; }
+            ctx->p = keep;
+        } else {
+            // fwdpush / montecarlo: the plain query, then topk_ppr (query.h:1141-1167)
+            std::vector<fora_query_stat> st(cnt);
+            if ((rc = query_batch_impl(ctx, algo, sources + q0, nullptr, cnt, nullptr, st.data(), nullptr))) return restore(rc);
+            if (stats) for (int s = 0; s < cnt; ++s) stats[q0 + s] = st[s];
+        }
+        CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+        for (int s = 0; s < cnt; ++s) { // topk_ppr(), algo.h:592-610
+            cudaError_t e = topk_device(ctx->stream, ctx->num_sms, result + nn * s, n, k, nodes + (size_t)(q0 + s) * k, values + (size_t)(q0 + s) * k, &ctx->launches);
+            if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("topk: ") + cudaGetErrorString(e)));
+        }
+        CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev[7]));
+        float t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
+        topk_ms += t;
+        if (algo == FORA_ALGO_FORA) {
+            if ((rc = meta_d2h_sync(ctx))) return restore(rc);
+            for (int s = 0; s < cnt; ++s) {
+                if (iters) iters[q0 + s] = it[s];
+                if (stats) {
+                    fill_stat(ctx, s, fr[s], rounds[s], &stats[q0 + s]);
+                    stats[q0 + s].n_walks = tot_walks[s]; stats[q0 + s].n_idx_hits = tot_hits[s]; stats[q0 + s].walk_hops = tot_hops[s];
+                }
+            }
+        } else if (iters) {
+            for (int s = 0; s < cnt; ++s) iters[q0 + s] = 1;
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[5], ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev[5]));
+    if (timing) {
+        memset(timing, 0, sizeof *timing);
+        CK(cudaEventElapsedTime(&timing->total_ms, ctx->ev[0], ctx->ev[5]));
+        timing->topk_ms = topk_ms;
+        timing->kernel_launches = ctx->launches - launches0;
+        timing->push_kernel_ms = (float)ctx->push_kernel_ms; timing->walk_kernel_ms = (float)ctx->walk_kernel_ms;
+        timing->push_kernel_launches = ctx->push_kernel_launches; timing->walk_kernel_launches = ctx->walk_kernel_launches;
+    }
+    return restore(FORA_OK);
 }
 
 // =============================================================================================
@@ -999,10 +1216,6 @@ extern "C" int fora_power_iteration(fora_ctx* ctx, int32_t source, int iters, do
 // =============================================================================================
 extern "C" int fora_reverse_push(fora_ctx* ctx, int32_t, double, double*, double*) {
     return ctx ? ctx->fail(FORA_EINVAL, "fora_reverse_push: not implemented in this build") : FORA_EINVAL;
-}
-extern "C" int fora_topk_batch(fora_ctx* ctx, int, const int32_t*, int32_t, uint32_t, int32_t*, double*, int32_t*,
-                               fora_query_stat*, fora_batch_timing*) {
-    return ctx ? ctx->fail(FORA_EINVAL, "fora_topk_batch: not implemented in this build") : FORA_EINVAL;
 }
 
 // development aid: copy the per-level trace of the last push launch (FORA_PUSH_TRACE=1); returns levels

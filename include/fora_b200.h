@@ -109,8 +109,11 @@ typedef struct fora_query_stat {
 } fora_query_stat;
 
 typedef struct fora_batch_timing { /* GPU milliseconds, CUDA events on the work stream */
-    float total_ms, push_ms, walk_ms, plan_ms, topk_ms, copy_ms;
+    float total_ms, push_ms, walk_ms, plan_ms, topk_ms, copy_ms; /* phases (push_ms includes seeding + host round trips) */
     uint64_t kernel_launches;
+    /* the two hot kernels alone, summed over their launches (roofline accounting) */
+    float push_kernel_ms, walk_kernel_ms;
+    uint64_t push_kernel_launches, walk_kernel_launches;
 } fora_batch_timing;
 
 /* ------------------------------------------------------------------------------------------

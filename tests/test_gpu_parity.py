@@ -346,6 +346,61 @@ def test_topk_select(g, eng):
         assert np.array_equal(vals, exp_vals) and np.array_equal(nodes, exp_nodes), k
 
 
+@pytest.mark.parametrize("with_idx", [0, 1])
+def test_topk_batch_fora_opt(with_idx):
+    # fora_query_topk_new (query.h:972-1045): precision against power iteration, and against the oracle's
+    # restatement of the same driver (north_star: within 0.01 of the reference on average; small graph here)
+    g2 = Graph.synth(6000, 72000, seed=13)
+    k = 50
+    E = fb.Engine(0, seed=4, slots=3)
+    E.upload_graph(g2.n, g2.m_decl, g2.out_ptr, g2.out_col)
+    rmax, omega = E.configure("fora", EPS, opt=1, k=k, with_idx=with_idx)
+    if with_idx:
+        off, cnt, total = E.index_info()
+        E.index_upload(off, cnt, E.index_build(off, cnt))
+    srcs = np.array([21, 5, 300, int(np.argmax(g2.deg)), int(np.flatnonzero(g2.deg == 0)[0]), 77, 1234], np.int32)
+    nodes, vals, iters, stats, tm = E.topk_batch("fora", srcs, k)
+    O = Oracle(g2, seed=8)
+    O.set_params(EPS, 0.0, 0.0, opt=1, k=k, with_idx=with_idx)
+    O.init_state(-9.0, 1)
+    if with_idx:
+        O.index_set(off, cnt, E.index_build(off, cnt))
+    prec_gpu, prec_orc = [], []
+    for i, s in enumerate(srcs):
+        exact = O.power_iteration(int(s), 150)
+        top = np.argsort(-exact, kind="stable")[:k]
+        npos = int((exact > 0).sum())
+        assert (np.diff(vals[i]) <= 0).all()
+        if g2.deg[s] == 0:
+            assert nodes[i][0] == s and vals[i][0] == 1.0 and (vals[i][1:] == 0).all() and iters[i] >= 1
+            continue
+        assert iters[i] >= 1 and stats[i]["n_walks"] > 0
+        kk = min(k, npos)
+        prec_gpu.append(len(set(nodes[i][:kk].tolist()) & set(top[:kk].tolist())) / kk)
+        O.fora_topk_new(int(s), 0)
+        on, ov = O.topk_ppr(k)
+        prec_orc.append(len(set(on[:kk].tolist()) & set(top[:kk].tolist())) / kk)
+        if with_idx:
+            assert stats[i]["n_idx_hits"] > 0
+    assert np.mean(prec_gpu) > 0.9 and abs(np.mean(prec_gpu) - np.mean(prec_orc)) < 0.05, (prec_gpu, prec_orc)
+    assert tm["topk_ms"] > 0
+    with pytest.raises(fb.ForaError):
+        E.topk_batch("fora", srcs, 1)            # 1 < k < n-1 (query.h:1317-1318)
+    E.close()
+
+
+def test_topk_batch_baselines(g, eng):
+    k = 30
+    O = Oracle(g)
+    s = 11
+    exact = O.power_iteration(s, 150)
+    top = set(np.argsort(-exact, kind="stable")[:k].tolist())
+    for algo in ("montecarlo", "fwdpush"):
+        eng.configure(algo, EPS, k=k)
+        nodes, vals, iters, stats, tm = eng.topk_batch(algo, np.array([s], np.int32), k)
+        assert len(set(nodes[0].tolist()) & top) / k > 0.85 and (np.diff(vals[0]) <= 0).all()
+
+
 def test_power_iteration_matches_golden(gold):
     n = int(gold["n"])
     g2 = Graph(n, gold["src"], gold["dst"], int(gold["m_decl"]))
