@@ -12,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "bippr.cuh"
 #include "common.cuh"
 #include "push.cuh"
 #include "topk.cuh"
@@ -111,6 +112,10 @@ struct fora_ctx {
     bool has_index = false;
     // scratch
     DevBuf<u64> counts;
+    // backward push scratch (bippr.cuh)
+    DevBuf<double> bwd_res, bwd_rv;
+    DevBuf<int32_t> bwd_lists;
+    int bwd_blocks = 0;
     DevBuf<u64> scratch64;
     DevBuf<int32_t> scratch32;
     DevBuf<double> scratchd;
@@ -221,7 +226,7 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
     ctx->ppr.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
-    ctx->counts.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
+    ctx->counts.release(); ctx->bwd_res.release(); ctx->bwd_rv.release(); ctx->bwd_lists.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->kev_pool) cudaEventDestroy(ev);
@@ -832,6 +837,101 @@ extern "C" int fora_compute_ppr(fora_ctx* ctx, const double* reserve, const doub
     return FORA_OK;
 }
 
+
+// =============================================================================================
+// backward push / BiPPR
+// =============================================================================================
+static int ensure_bwd(fora_ctx* ctx) {
+    const DeviceGraph& g = ctx->g;
+    if (!g.has_in) return ctx->fail(FORA_EINVAL, "backward push needs the in-CSR (fora_graph_upload with in_ptr/in_col)");
+    const size_t n = (size_t)g.n;
+    if (ctx->bwd_blocks && ctx->bwd_res.cap >= n * ctx->bwd_blocks) return FORA_OK;
+    const size_t per_block = 32 * n; // bytes
+    int nb = (int)std::min<size_t>((size_t)ctx->num_sms * 4, std::max<size_t>(4, ((size_t)8 << 30) / per_block));
+    CK(ctx->bwd_res.ensure(n * nb));
+    CK(ctx->bwd_rv.ensure(n * nb));
+    CK(ctx->bwd_lists.ensure(4 * n * nb));
+    CK(cudaMemsetAsync(ctx->bwd_res.p, 0, sizeof(double) * n * nb, ctx->stream));
+    ctx->bwd_blocks = nb;
+    return FORA_OK;
+}
+
+// run the backward pushes of targets [t_begin, t_end) of one query; counts/ppr may be null (test hook)
+static int launch_bwd(fora_ctx* ctx, int32_t source, double rmax, double omega, const u64* counts, double* ppr, int32_t t_begin,
+                      int32_t t_end, double* full_reserve, int keep_residue, u64* d_edges, int32_t* d_overflow) {
+    const DeviceGraph& g = ctx->g;
+    const int nb = keep_residue ? 1 : std::min(ctx->bwd_blocks, std::max(1, t_end - t_begin));
+    if (g.off32) {
+        BwdArgs<u32> a{g.n, ctx->p.alpha, rmax, omega, source, g.in_ptr32, g.in_col, g.deg, counts, ctx->bwd_res.p, ctx->bwd_rv.p,
+                       ctx->bwd_lists.p, d_overflow, ppr, t_begin, t_end, full_reserve, keep_residue, d_edges};
+        bippr_kernel<u32><<<nb, BWD_THREADS, 0, ctx->stream>>>(a);
+    } else {
+        BwdArgs<int64_t> a{g.n, ctx->p.alpha, rmax, omega, source, g.in_ptr64, g.in_col, g.deg, counts, ctx->bwd_res.p, ctx->bwd_rv.p,
+                           ctx->bwd_lists.p, d_overflow, ppr, t_begin, t_end, full_reserve, keep_residue, d_edges};
+        bippr_kernel<int64_t><<<nb, BWD_THREADS, 0, ctx->stream>>>(a);
+    }
+    CKL();
+    return FORA_OK;
+}
+
+extern "C" int fora_reverse_push(fora_ctx* ctx, int32_t target, double rmax, double* reserve, double* residue) {
+    if (!ctx || !ctx->g.n) return ctx ? ctx->fail(FORA_EINVAL, "no graph") : FORA_EINVAL;
+    if (target < 0 || target >= ctx->g.n) return ctx->fail(FORA_EINVAL, "target out of range");
+    CK(cudaSetDevice(ctx->device));
+    int rc = ensure_bwd(ctx);
+    if (rc) return rc;
+    const size_t n = (size_t)ctx->g.n;
+    CK(ctx->scratchd.ensure(n));
+    CK(ctx->scratch32.ensure(4));
+    CK(cudaMemsetAsync(ctx->scratchd.p, 0, sizeof(double) * n, ctx->stream));
+    CK(cudaMemsetAsync(ctx->scratch32.p, 0, sizeof(int32_t) * 4, ctx->stream));
+    if ((rc = launch_bwd(ctx, -1, rmax, 1.0, nullptr, nullptr, target, target + 1, ctx->scratchd.p, 1, nullptr, ctx->scratch32.p))) return rc;
+    if (reserve) CK(cudaMemcpyAsync(reserve, ctx->scratchd.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (residue) CK(cudaMemcpyAsync(residue, ctx->bwd_res.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    // the hook left block 0's scratch dirty: wipe it (dense memset, test path only)
+    CK(cudaMemsetAsync(ctx->bwd_res.p, 0, sizeof(double) * n, ctx->stream));
+    int32_t ovf = 0;
+    CK(cudaMemcpyAsync(&ovf, ctx->scratch32.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ovf) return ctx->fail(FORA_ECUDA, "backward push: touched list overflow");
+    return FORA_OK;
+}
+
+// bippr_query (query.h:71-124) for one source; result in d_ppr (device double[n])
+static int bippr_one(fora_ctx* ctx, int32_t source, u32 qid, double* d_ppr, u64* n_walks, u64* hops, u64* edges) {
+    const size_t n = (size_t)ctx->g.n;
+    const fora_params& p = ctx->p;
+    int rc;
+    CK(ctx->counts.ensure(n));
+    CK(ctx->scratch64.ensure(4));
+    CK(ctx->scratch32.ensure(4));
+    CK(cudaMemsetAsync(ctx->counts.p, 0, sizeof(u64) * n, ctx->stream));
+    CK(cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(u64) * 4, ctx->stream));
+    CK(cudaMemsetAsync(ctx->scratch32.p, 0, sizeof(int32_t) * 4, ctx->stream));
+    const u64 nw = (u64)ceil(p.omega); // for(i=0; i<omega; i++), query.h:81
+    BulkArgs ba{};
+    ba.alpha_thr = (u32)std::min(4294967295.0, p.alpha * 4294967296.0);
+    ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
+    ba.key_tag = 0x42500000u + qid;
+    ba.single = source; ba.total = nw; ba.dest = nullptr; ba.counts = ctx->counts.p; ba.hops = ctx->scratch64.p;
+    if ((rc = launch_bulk(ctx, ba, 0))) return rc;
+    if (p.rmax < 1.0) { // query.h:91
+        if ((rc = ensure_bwd(ctx))) return rc;
+        if ((rc = launch_bwd(ctx, source, p.rmax, p.omega, ctx->counts.p, d_ppr, 0, ctx->g.n, nullptr, 0, ctx->scratch64.p + 1, ctx->scratch32.p))) return rc;
+    } else {            // query.h:114-119
+        counts_to_ppr_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->g.n, ctx->counts.p, p.omega, d_ppr);
+        CKL();
+    }
+    u64 h2[2];
+    int32_t ovf = 0;
+    CK(cudaMemcpyAsync(h2, ctx->scratch64.p, sizeof(u64) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&ovf, ctx->scratch32.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ovf) return ctx->fail(FORA_ECUDA, "backward push: touched list overflow");
+    *n_walks = nw; *hops = h2[0]; *edges = h2[1];
+    return FORA_OK;
+}
+
 // =============================================================================================
 // queries
 // =============================================================================================
@@ -840,8 +940,9 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
     int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
     if (rc) return rc;
     if (n_q < 0 || (!h_sources && !d_sources && n_q)) return ctx->fail(FORA_EINVAL, "bad sources");
-    if (algo != FORA_ALGO_FORA && algo != FORA_ALGO_FWDPUSH && algo != FORA_ALGO_MC)
-        return ctx->fail(FORA_EINVAL, "algo not supported by fora_query_batch (bippr: see fora_bippr_query)");
+    if (algo != FORA_ALGO_FORA && algo != FORA_ALGO_FWDPUSH && algo != FORA_ALGO_MC && algo != FORA_ALGO_BIPPR)
+        return ctx->fail(FORA_EINVAL, "unknown algo");
+    if (algo == FORA_ALGO_BIPPR && d_sources) return ctx->fail(FORA_EINVAL, "bippr: host sources only");
     const size_t n = (size_t)ctx->g.n;
     const int S = ctx->slots;
     ctx->session_source = -1;
@@ -874,6 +975,16 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
             ctx->p.balanced = keep;
             if (rc) return rc;
             CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+        } else if (algo == FORA_ALGO_BIPPR) { // query.h:71-124
+            CK(cudaEventRecord(ctx->ev[2], ctx->stream));
+            for (int s = 0; s < MAX_SLOTS; ++s) { h->state[s] = 0; h->nwalk[s] = h->hops[s] = h->edges[s] = h->vertices[s] = h->levels[s] = h->nsrc[s] = h->idx_hits[s] = 0; h->rsum[s] = 0; }
+            for (int s = 0; s < cnt; ++s) {
+                u64 nw, hp, ed;
+                if ((rc = bippr_one(ctx, h->source[s], h->qid[s], ctx->reserve.p + n * s, &nw, &hp, &ed))) return rc;
+                h->nwalk[s] = nw; h->hops[s] = hp; h->edges[s] = ed; h->state[s] = 1;
+                rounds[s] = 0;
+            }
+            if ((rc = meta_h2d(ctx))) return rc;
         } else { // Monte-Carlo, query.h:16-43: omega walks from the source, ppr = count/omega
             if ((rc = init_wave(ctx, cnt, 0, d_sources ? d_sources + q0 : nullptr))) return rc;
             if ((rc = meta_d2h_sync(ctx))) return rc;
@@ -966,7 +1077,6 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
     const int32_t n = ctx->g.n;
     if (!(k > 1 && (int64_t)k < (int64_t)n - 1)) return ctx->fail(FORA_EINVAL, "k must satisfy 1 < k < n-1 (query.h:1317-1318)");
     if (!sources || !nodes || !values || n_q < 0) return ctx->fail(FORA_EINVAL, "bad arguments");
-    if (algo == FORA_ALGO_BIPPR) return ctx->fail(FORA_EINVAL, "bippr top-k: use fora_bippr_query + fora_topk_of");
     const fora_params keep = ctx->p;
     int rc = FORA_OK;
     auto restore = [&](int code) { ctx->p = keep; return code; };
@@ -1214,9 +1324,6 @@ extern "C" int fora_power_iteration(fora_ctx* ctx, int32_t source, int iters, do
 // =============================================================================================
 // not yet wired (fail loudly rather than fall back)
 // =============================================================================================
-extern "C" int fora_reverse_push(fora_ctx* ctx, int32_t, double, double*, double*) {
-    return ctx ? ctx->fail(FORA_EINVAL, "fora_reverse_push: not implemented in this build") : FORA_EINVAL;
-}
 
 // development aid: copy the per-level trace of the last push launch (FORA_PUSH_TRACE=1); returns levels
 extern "C" int fora_debug_push_trace(fora_ctx* ctx, uint64_t* out, int cap_levels) {

@@ -294,6 +294,52 @@ def test_montecarlo_and_fwdpush(g, eng):
     assert (ppr[0] <= exact + 1e-12).all() and np.average(np.abs(ppr[0][big] - exact[big]) / exact[big]) < 0.5
 
 
+def test_reverse_push_matches_oracle(g, eng, gold):
+    # reverse_local_update_linear (algo.h:703-751) on the frontier-synchronous schedule
+    eng.configure("bippr", EPS)
+    O = Oracle(g)
+    for rm in (0.3, 1e-2, 1e-4, 2.0):
+        for t in interesting_sources(g):
+            res, rsd = eng.reverse_push(t, rm)
+            O.reverse_push(t, rm, 1.0, 1)
+            a, b = O.bwd()
+            assert relerr(res, a) < PUSH_RTOL and relerr(rsd, b) < PUSH_RTOL, (rm, t)
+    # on the golden graph a shallow push (rmax = 0.3) visits every vertex at most once, so the reference's
+    # FIFO result (golden) and the synchronous schedule coincide up to summation order
+    n = int(gold["n"])
+    g2 = Graph(n, gold["src"], gold["dst"], int(gold["m_decl"]))
+    E = fb.Engine(0)
+    E.upload_graph(n, g2.m_decl, g2.out_ptr, g2.out_col, g2.in_ptr, g2.in_col)
+    E.configure("bippr", float(gold["eps"]))
+    res, rsd = E.reverse_push(int(gold["sources"][1]), float(gold["bwd_rmax_0"]))
+    assert np.allclose(res, gold["bwd_reserve_0"], rtol=1e-12, atol=0) and np.allclose(rsd, gold["bwd_residue_0"], rtol=1e-12, atol=0)
+    E2 = fb.Engine(0)
+    E2.upload_graph(n, g2.m_decl, g2.out_ptr, g2.out_col)  # no in-CSR
+    E2.configure("bippr", float(gold["eps"]))
+    with pytest.raises(fb.ForaError, match="in-CSR"):
+        E2.reverse_push(0, 0.3)
+    E.close(); E2.close()
+
+
+def test_bippr_query(g, eng):
+    # bippr_query (query.h:71-124): omega walks + one backward push per target node
+    rmax, omega = eng.configure("bippr", EPS)
+    assert rmax < 1.0
+    O = Oracle(g)
+    srcs = np.array([11, 0], np.int32)
+    ppr, stats, _ = eng.query_batch("bippr", srcs)
+    for i, s in enumerate(srcs):
+        exact = O.power_iteration(int(s), 150)
+        big = exact >= 1.0 / g.n
+        assert stats[i]["n_walks"] == int(np.ceil(omega))
+        assert (np.abs(ppr[i][big] - exact[big]) / exact[big]).max() < 1.0
+        assert np.median(np.abs(ppr[i][big] - exact[big]) / exact[big]) < 0.15
+    # rmax >= 1 falls back to pure Monte-Carlo (query.h:114-120)
+    eng.set_params(EPS, 1.5, omega)
+    ppr2, st2, _ = eng.query_batch("bippr", srcs[:1])
+    assert abs(ppr2[0].sum() - np.ceil(omega) / omega) < 1e-9
+
+
 # ------------------------------------------------------------------------------------ index
 def test_index_layout_bit_exact_and_with_idx_queries(gold):
     n = int(gold["n"])
