@@ -246,9 +246,10 @@ def main():
 
     B = args.batch
     # weak scaling: every rank processes B queries per step, its own shard of a world*B global batch
+    from fora_b200 import shard
+
     def step_ids(i):
-        base = (i * B * world + rank * B) % N_QUERIES
-        return np.array([queries[(base + j) % N_QUERIES] for j in range(B)], np.int32)
+        return shard.step_query_ids(queries, i, B, rank, world)[0]
 
     steps_total = args.warmup + args.steps
     d_src = [torch.from_numpy(step_ids(i)).cuda() for i in range(steps_total)]
@@ -277,10 +278,7 @@ def main():
     ev1.record(stream)
     barrier()
     clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = shard.max_over_ranks(ev0.elapsed_time(ev1))
     value = world * B * args.steps / (ms_total / 1e3)
 
     # ---- e2e: host buffers in, dense PPR vectors out (pinned), copies inside the timed region
@@ -295,10 +293,7 @@ def main():
     _, st_e2e, _ = E.query_batch("fora", src_np, out=ppr_np)
     e1.record(stream)
     barrier()
-    ms2 = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = world * nq / (float(ms2.item()) / 1e3)
+    e2e_value = world * nq / (shard.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
     checksum = float(ppr_np.sum(axis=1).mean())  # each PPR vector sums to 1
 
     if rank == 0:

@@ -11,7 +11,7 @@
 // push: a vertex is pushed when its residue is >= r_max at level 0 (algo.h:725) and joins the next
 // level when a scatter moves its residue from <= r_max to > r_max (algo.h:743).  The reference's
 // early `break` (algo.h:725-726) and its double counting of re-inserted keys
-// are deliberately not reproduced; oracle/fora_oracle.c restates both variants.
+// are deliberately not reproduced; the test suite checks both variants.
 #pragma once
 #include "common.cuh"
 
