@@ -190,7 +190,6 @@ extern "C" int fora_ctx_create(int device, uint64_t seed, fora_ctx** out) {
     ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     ctx->l2_policy = getenv("FORA_NO_L2_POLICY") == nullptr && ctx->l2_persist_max > 0;
-    if (ctx->l2_policy) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, ctx->l2_persist_max);
     if (!prop.cooperativeLaunch) {
         g_create_error = "device lacks cooperative launch";
         delete ctx;
@@ -377,10 +376,12 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
             ctx->win_push_bytes = b_res + b_deg;
             ctx->win_walk_off = b_res + b_deg;
             ctx->win_walk_bytes = b_ptr + b_res;
-            if (ctx->win_push_bytes > ctx->l2_persist_max) { ctx->win_push_off = b_res; ctx->win_push_bytes = b_deg + b_ptr; }
-            if (ctx->win_walk_bytes > ctx->l2_persist_max) { ctx->win_walk_off = b_res; ctx->win_walk_bytes = b_deg + b_ptr; }
-            if (ctx->win_push_bytes > ctx->l2_persist_max) ctx->win_push_bytes = 0; // huge graphs: leave the L2 alone
-            if (ctx->win_walk_bytes > ctx->l2_persist_max) ctx->win_walk_bytes = 0;
+            // The persisting carve-out is taken away from the normal L2 (79 of 126 MB on B200), so it only
+            // pays when the pinned arrays fit: one slot at LiveJournal scale.  Otherwise leave the L2 alone
+            // (measured: 4 slots 134 q/s without a window vs 90 q/s with deg+offsets pinned).
+            const bool fits = ctx->l2_policy && ctx->win_push_bytes <= ctx->l2_persist_max && ctx->win_walk_bytes <= ctx->l2_persist_max;
+            if (!fits) ctx->win_push_bytes = ctx->win_walk_bytes = 0;
+            if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, fits ? ctx->l2_persist_max : 0);
         }
         CK(ctx->front0.ensure(fcap));
         CK(ctx->front1.ensure(fcap));
@@ -425,7 +426,7 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
 
 // Pin [arena+off, +bytes) in L2 for the kernels launched next on the work stream (bytes == 0 clears).
 static int set_l2_window(fora_ctx* ctx, size_t off, size_t bytes) {
-    if (!ctx->l2_policy) return FORA_OK;
+    if (!ctx->l2_policy || bytes == 0) return FORA_OK;
     cudaStreamAttrValue av;
     memset(&av, 0, sizeof av);
     if (bytes) {

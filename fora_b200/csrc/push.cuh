@@ -315,10 +315,15 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
             for (int k = 0; k < PUSH_UB; ++k) {
                 bool cross = false;
                 if (ok[k]) {
+                    // the out-degree is only needed if the add can have crossed rmax*d (d >= 1 => nw >= rmax)
+                    // or was a first touch (a dangling vertex joins on any positive residue): ~half the edges
                     const double nw = old[k] + inc[k];
-                    const int32_t du = __ldg(&a.deg[u[k]]);
-                    const double thr = sm.rmax[slot[k]] * (double)du;
-                    cross = du ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
+                    const double rm = sm.rmax[slot[k]];
+                    if (nw >= rm || old[k] == 0.0) {
+                        const int32_t du = __ldg(&a.deg[u[k]]);
+                        const double thr = rm * (double)du;
+                        cross = du ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
+                    }
                 }
                 const u32 m = __ballot_sync(FULL, cross);
                 if (cross) myq[wq + __popc(m & lanemask_lt())] = ((u64)slot[k] << 32) | (u32)u[k];
