@@ -510,6 +510,8 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     a.level_base = ctx->level_base;
     a.trace = ctx->trace_on ? ctx->trace.p : nullptr;
     a.trace_cap = ctx->trace_on ? 4096 : 0;
+    a.tile_max = getenv("FORA_TILE_MAX") ? (u32)atoi(getenv("FORA_TILE_MAX")) : TILE_MAX;
+    a.l2_hints = getenv("FORA_L2_HINTS") ? (u32)atoi(getenv("FORA_L2_HINTS")) : 1u;
     return a;
 }
 

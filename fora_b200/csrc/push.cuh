@@ -12,9 +12,10 @@
 //
 // One persistent cooperative kernel runs every level of every query slot of a batch; the
 // frontier test and termination live on the device.  Work is edge-balanced across the grid: the
-// edges of a level are laid on one line (exclusive scan of the frontier's out-degrees) and cut
-// into equal slices, one per CTA, so a power-law hub is simply split across CTAs and no warp
-// ever waits for a straggler; column reads are coalesced.
+// edges of a level are laid on one slot-major line (exclusive scan of the frontier's out-degrees) and
+// cut into tiles that the CTAs take round-robin, so a power-law hub is simply split across CTAs, no
+// warp waits for a straggler, and the grid sweeps one or two slots' residue vectors at a time (they stay
+// L2-resident although a wave holds many slots and all slots share each level's two barriers).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -27,16 +28,17 @@ constexpr int PUSH_THREADS = 512;
 constexpr int PUSH_WARPS = PUSH_THREADS / WARP;
 constexpr int MAX_SLOTS = 64;
 constexpr int MAX_PUSH_CTAS = 512;
-constexpr u32 MIN_PIECE = 1024;  // smallest edge range worth giving to a CTA
+constexpr u32 TILE_MIN = 2048;   // smallest edge range worth giving to a CTA
+constexpr u32 TILE_MAX = 16384;  // tiles of a large level: the grid sweeps the edge line 296*16K edges at a time
 constexpr int PUSH_UA = 4;       // frontier entries per thread per phase-A batch
 constexpr int PUSH_BATCH = 1024; // frontier entries staged in shared memory per phase-B batch
 constexpr int PUSH_UB = 4;       // edges in flight per lane in phase B
 constexpr int PUSH_WQ = 256;     // per-warp queue of crossing vertices
 
 struct PushCtl {
-    u32 fcount[3];   // frontier sizes, rotated by level % 3
+    u32 fcount[3][MAX_SLOTS]; // per-slot frontier sizes, rotated by level % 3
     u32 levels_run;
-    u32 pad[4];
+    u32 pad[3];
 };
 
 struct PushArgs {
@@ -46,9 +48,9 @@ struct PushArgs {
     double* reserve;  // [slots*n]   (mutated across levels: no __restrict__, read with __ldcg)
     double* residue;  // [slots*n]
     const int32_t* __restrict__ deg;
-    u64* front0;      // (slot<<32 | v)
+    u64* front0;      // [slots*n]: slot s owns [s*n, (s+1)*n); entries (slot<<32 | v)
     u64* front1;
-    double* inc;      // per frontier entry: ((1-alpha)*r)/d, or (1-alpha)*r when dangling
+    double* inc;      // per frontier entry (global index): ((1-alpha)*r)/d, or (1-alpha)*r when dangling
     u32* eoff;        // per frontier entry: edge offset inside its CTA chunk
     u64* block_sum;   // [gridDim.x] edges per CTA chunk of the current level
     PushCtl* ctl;
@@ -63,6 +65,8 @@ struct PushArgs {
     u32 level_base;                      // distinguishes levels of successive launches in lastlvl
     u64* trace;                          // optional [4*trace_cap]: per level {t0 ns, nf, E, t after phase A}
     u32 trace_cap;
+    u32 tile_max;                        // edges per tile of a large level
+    u32 l2_hints;                        // 1: evict_last on residue atomics / degree loads, evict_first on streams
 };
 
 // dynamic shared memory of the push kernel (~70 KB, two CTAs per SM)
@@ -78,8 +82,39 @@ struct PushSmem {
     double rmax[MAX_SLOTS];
     int32_t source[MAX_SLOTS];
     u32 cnt_edges[MAX_SLOTS], cnt_verts[MAX_SLOTS];
+    u32 fbase[MAX_SLOTS + 1];    // the level's frontier = the slots' segments concatenated in slot order
     u32 i0;
 };
+
+
+// L2 eviction-priority hints (sm_80+ createpolicy / .L2::cache_hint): the vectors every edge touches at
+// random (residue, out-degree) are kept with evict_last, everything streamed once per level goes through
+// with evict_first -- pinning without giving up a fixed carve-out of the L2.
+__device__ __forceinline__ u64 l2_policy_evict_last() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ u64 l2_policy_evict_first() {
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ double atomic_add_f64_hint(double* addr, double v, u64 policy) {
+    double old;
+    asm volatile("atom.global.add.L2::cache_hint.f64 %0, [%1], %2, %3;" : "=d"(old) : "l"(addr), "d"(v), "l"(policy) : "memory");
+    return old;
+}
+__device__ __forceinline__ int32_t ld_s32_hint(const int32_t* addr, u64 policy) {
+    int32_t v;
+    asm volatile("ld.global.nc.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(addr), "l"(policy));
+    return v;
+}
+__device__ __forceinline__ int32_t ld_col_stream(const int32_t* addr, u64 policy) {
+    int32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(addr), "l"(policy));
+    return v;
+}
 
 // block-wide inclusive scan of one u64 per thread; returns the inclusive value, *total = block sum
 template <typename OffT>
@@ -100,6 +135,18 @@ __device__ __forceinline__ u64 block_incl_scan(PushSmem<OffT>& sm, u64 v, u64* t
     return incl;
 }
 
+// frontier entry i of the level (slot-major concatenation of the per-slot segments)
+template <typename OffT>
+__device__ __forceinline__ u64 frontier_entry(const PushArgs& a, const PushSmem<OffT>& sm, const u64* cur, u32 i) {
+    int lo = 0, hi = a.slots; // last slot with fbase[slot] <= i
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sm.fbase[mid] <= i) lo = mid;
+        else hi = mid;
+    }
+    return __ldcs(&cur[(size_t)lo * a.n + (i - sm.fbase[lo])]);
+}
+
 // ---- phase A: CTA `rank` of `count` takes a contiguous chunk of the frontier: snapshot + zero the
 // residues, credit the reserves, and lay the chunk's edges out on a line (eoff = exclusive scan
 // of the out-degrees; a dangling vertex owns one pseudo-edge back to its slot's source).
@@ -117,7 +164,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
         double r[PUSH_UA], rs[PUSH_UA];
         u32 d[PUSH_UA];
 #pragma unroll
-        for (int k = 0; k < PUSH_UA; ++k) e[k] = (i0 + k < hi_i) ? __ldcs(&cur[i0 + k]) : ~0ull;
+        for (int k = 0; k < PUSH_UA; ++k) e[k] = (i0 + k < hi_i) ? frontier_entry(a, sm, cur, i0 + k) : ~0ull;
 #pragma unroll
         for (int k = 0; k < PUSH_UA; ++k) {
             r[k] = rs[k] = 0.0;
@@ -187,14 +234,28 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
     }
 }
 
-// ---- phase B: the level's edges form one line of length E (chunk bases + eoff); CTA `rank` owns
-// the slice [rank*P, (rank+1)*P): perfectly edge-balanced whatever the degree distribution, a
-// hub is simply cut across CTAs.  Entries are staged PUSH_BATCH at a time in shared memory; inside
-// a batch the warps run independently (no CTA barrier in the edge loop): a warp step covers
-// 32*PUSH_UB consecutive edges, every lane keeps PUSH_UB scatters in flight, owners are found by
-// binary search in shared memory, column reads are coalesced and streamed past the L2-resident
-// residue vector, and crossing vertices collect in a private per-warp queue that is appended to
-// the next frontier with one global atomic per flush.
+// append this warp's queue (entries of ONE slot) to that slot's segment of the next frontier
+__device__ __forceinline__ void push_flush_warp(const PushArgs& a, const u64* myq, u32 wq, int wq_slot, u64* nxt, u32* nxt_count) {
+    const int lane = lane_id();
+    u32 base = 0;
+    __syncwarp();
+    if (lane == 0) base = atomicAdd(&nxt_count[wq_slot], wq);
+    base = __shfl_sync(FULL, base, 0);
+    u64* dst = nxt + (size_t)wq_slot * a.n + base;
+    for (u32 t = lane; t < wq; t += WARP) dst[t] = myq[t];
+    __syncwarp();
+}
+
+// ---- phase B: the level's edges form one line of length E (chunk bases + eoff), slot-major because
+// the frontier is.  The line is cut into tiles; CTA `rank` takes tiles rank, rank+count, ...: work is
+// perfectly edge-balanced whatever the degree distribution (a hub is simply cut across tiles) and the
+// whole grid sweeps the line front to back together, so at any moment it touches the residue vectors
+// of one or two slots only -- they stay L2-resident although a wave holds many slots.  Entries are staged
+// PUSH_BATCH at a time in shared memory; inside a batch the warps run independently (no CTA barrier in
+// the edge loop): a warp step covers 32*PUSH_UB consecutive edges, every lane keeps PUSH_UB scatters in
+// flight, owners are found by binary search in shared memory, column reads are coalesced and streamed,
+// and crossing vertices collect in a private per-warp queue that is appended to the slot's next
+// frontier with one global atomic per flush.
 template <typename OffT>
 __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<OffT>& g, PushSmem<OffT>& sm, const u64* cur,
                                              u32 nf, u32 level, u32 rank, u32 count, u64* nxt, u32* nxt_count) {
@@ -217,131 +278,138 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
     const u64 E = sm.base[count];
     if (a.trace && rank == 0 && threadIdx.x == 0 && level < a.trace_cap) a.trace[4 * level + 2] = E;
     if (E == 0) return;
-    u64 P = (E + count - 1) / count;
-    if (P < MIN_PIECE) P = MIN_PIECE;
-    const u64 lo = (u64)rank * P;
-    if (lo >= E) return;
-    const u64 hi = min(E, lo + P);
-    // first entry of the slice: largest i with G(i) <= lo, G(i) = base[i / cs] + eoff[i]
-    if (w == 0) {
-        u32 c = 0; // largest chunk with base[c] <= lo (only trailing chunks are empty, and they sit at E)
-        {
-            u32 l = 0, h = count;
-            while (h - l > 1) {
-                const u32 mid = (l + h) >> 1;
-                if (sm.base[mid] <= lo) l = mid;
-                else h = mid;
-            }
-            c = l;
-        }
-        const u64 target = lo - sm.base[c];
-        u32 l = min(nf, c * cs), h = min(nf, l + cs); // answer in [l, h), eoff[l] == 0 <= target
-        while (h - l > 1) {                            // 32-ary search
-            const u32 span = h - l;
-            const u32 step = (span + WARP - 1) / WARP;
-            const u32 pos = l + lane * step;
-            const bool le = pos < h && (u64)__ldcg(&a.eoff[pos]) <= target;
-            const u32 m = __ballot_sync(FULL, le);
-            const int last = 31 - __clz(m); // lane 0 always satisfies
-            const u32 nl = l + last * step;
-            h = min(h, nl + step);
-            l = nl;
-        }
-        if (lane == 0) sm.i0 = l;
-    }
-    __syncthreads();
-    u32 i_cur = sm.i0;
-    u32 wq = 0; // entries in this warp's queue (warp-uniform register)
+    u64 T = (E + count - 1) / count;
+    T = T < TILE_MIN ? TILE_MIN : (T > a.tile_max ? a.tile_max : T);
+    const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
+    u32 wq = 0;       // entries in this warp's queue (warp-uniform register)
+    int wq_slot = 0;  // the slot they belong to
     u64* myq = sm.wqueue[w];
-    for (;;) {
-        const u32 cnt = min((u32)PUSH_BATCH, nf - i_cur);
-        for (u32 t = threadIdx.x; t <= cnt; t += PUSH_THREADS) {
-            const u32 i = i_cur + t;
-            if (t < cnt) {
-                const u64 e = __ldcs(&cur[i]);
-                const int slot = (int)(e >> 32);
-                const int32_t v = (int32_t)(u32)e;
-                const OffT beg = g.ptr[v];
-                const bool dang = g.ptr[v + 1] == beg;
-                sm.G[t] = sm.base[i / cs] + __ldcg(&a.eoff[i]);
-                sm.beg[t] = beg;
-                sm.inc[t] = __ldcg(&a.inc[i]);
-                sm.slot[t] = dang ? ~slot : slot;
-            } else {
-                sm.G[cnt] = i < nf ? sm.base[i / cs] + __ldcg(&a.eoff[i]) : E;
+    for (u64 lo = (u64)rank * T; lo < E; lo += (u64)count * T) {
+        const u64 hi = min(E, lo + T);
+        // first entry of the tile: largest i with G(i) <= lo, G(i) = base[i / cs] + eoff[i]
+        if (w == 0) {
+            u32 c = 0; // largest chunk with base[c] <= lo (only trailing chunks are empty, and they sit at E)
+            {
+                u32 l = 0, h = count;
+                while (h - l > 1) {
+                    const u32 mid = (l + h) >> 1;
+                    if (sm.base[mid] <= lo) l = mid;
+                    else h = mid;
+                }
+                c = l;
             }
+            const u64 target = lo - sm.base[c];
+            u32 l = min(nf, c * cs), h = min(nf, l + cs); // answer in [l, h), eoff[l] == 0 <= target
+            while (h - l > 1) {                            // 32-ary search
+                const u32 span = h - l;
+                const u32 step = (span + WARP - 1) / WARP;
+                const u32 pos = l + lane * step;
+                const bool le = pos < h && (u64)__ldcg(&a.eoff[pos]) <= target;
+                const u32 m = __ballot_sync(FULL, le);
+                const int last = 31 - __clz(m); // lane 0 always satisfies
+                const u32 nl = l + last * step;
+                h = min(h, nl + step);
+                l = nl;
+            }
+            if (lane == 0) sm.i0 = l;
         }
         __syncthreads();
-        const u64 x_lo = max(lo, sm.G[0]), x_hi = min(hi, sm.G[cnt]);
-        // warp w takes steps w, w + PUSH_WARPS, ... of 32*PUSH_UB consecutive edges
-        for (u64 xb = x_lo + (u64)w * (WARP * PUSH_UB); xb < x_hi; xb += (u64)PUSH_WARPS * WARP * PUSH_UB) {
-            if (wq > PUSH_WQ - WARP * PUSH_UB) { // make room: one global atomic per flush
-                u32 base = 0;
-                if (lane == 0) base = atomicAdd(nxt_count, wq);
-                base = __shfl_sync(FULL, base, 0);
-                for (u32 t = lane; t < wq; t += WARP) nxt[base + t] = myq[t];
-                __syncwarp();
-                wq = 0;
-            }
-            int slot[PUSH_UB];
-            int32_t u[PUSH_UB];
-            double inc[PUSH_UB], old[PUSH_UB];
-            bool ok[PUSH_UB];
-            u32 l = 0;
-#pragma unroll
-            for (int k = 0; k < PUSH_UB; ++k) {
-                const u64 x = xb + (u64)k * WARP + lane;
-                ok[k] = x < x_hi;
-                slot[k] = 0; u[k] = 0; inc[k] = 0.0;
-                if (ok[k]) {
-                    // largest t in [l, h) with G[t] <= x; after the first edge the owner moves forward by at
-                    // most 32 entries (every entry owns >= 1 edge)
-                    u32 h = k == 0 ? cnt : min(cnt, l + WARP + 1);
-                    while (h - l > 1) {
-                        const u32 mid = (l + h) >> 1;
-                        if (sm.G[mid] <= x) l = mid;
-                        else h = mid;
-                    }
-                    const int sj = sm.slot[l];
-                    slot[k] = sj < 0 ? ~sj : sj;
-                    inc[k] = sm.inc[l];
-                    u[k] = sj < 0 ? sm.source[slot[k]] : __ldcs(&g.col[sm.beg[l] + (OffT)(x - sm.G[l])]);
+        u32 i_cur = sm.i0;
+        for (;;) {
+            const u32 cnt = min((u32)PUSH_BATCH, nf - i_cur);
+            for (u32 t = threadIdx.x; t <= cnt; t += PUSH_THREADS) {
+                const u32 i = i_cur + t;
+                if (t < cnt) {
+                    const u64 e = frontier_entry(a, sm, cur, i);
+                    const int slot = (int)(e >> 32);
+                    const int32_t v = (int32_t)(u32)e;
+                    const OffT beg = g.ptr[v];
+                    const bool dang = g.ptr[v + 1] == beg;
+                    sm.G[t] = sm.base[i / cs] + __ldcg(&a.eoff[i]);
+                    sm.beg[t] = beg;
+                    sm.inc[t] = __ldcg(&a.inc[i]);
+                    sm.slot[t] = dang ? ~slot : slot;
+                } else {
+                    sm.G[cnt] = i < nf ? sm.base[i / cs] + __ldcg(&a.eoff[i]) : E;
                 }
             }
+            __syncthreads();
+            const u64 x_lo = max(lo, sm.G[0]), x_hi = min(hi, sm.G[cnt]);
+            // warp w takes steps w, w + PUSH_WARPS, ... of 32*PUSH_UB consecutive edges
+            for (u64 xb = x_lo + (u64)w * (WARP * PUSH_UB); xb < x_hi; xb += (u64)PUSH_WARPS * WARP * PUSH_UB) {
+                if (wq > PUSH_WQ - WARP * PUSH_UB) { // make room: one global atomic per flush
+                    push_flush_warp(a, myq, wq, wq_slot, nxt, nxt_count);
+                    wq = 0;
+                }
+                int slot[PUSH_UB];
+                int32_t u[PUSH_UB];
+                double inc[PUSH_UB], old[PUSH_UB];
+                bool ok[PUSH_UB];
+                u32 l = 0;
 #pragma unroll
-            for (int k = 0; k < PUSH_UB; ++k)
-                if (ok[k]) old[k] = atomicAdd(&a.residue[(size_t)slot[k] * a.n + u[k]], inc[k]);
-#pragma unroll
-            for (int k = 0; k < PUSH_UB; ++k) {
-                bool cross = false;
-                if (ok[k]) {
-                    // the out-degree is only needed if the add can have crossed rmax*d (d >= 1 => nw >= rmax)
-                    // or was a first touch (a dangling vertex joins on any positive residue): ~half the edges
-                    const double nw = old[k] + inc[k];
-                    const double rm = sm.rmax[slot[k]];
-                    if (nw >= rm || old[k] == 0.0) {
-                        const int32_t du = __ldg(&a.deg[u[k]]);
-                        const double thr = rm * (double)du;
-                        cross = du ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
+                for (int k = 0; k < PUSH_UB; ++k) {
+                    const u64 x = xb + (u64)k * WARP + lane;
+                    ok[k] = x < x_hi;
+                    slot[k] = 0; u[k] = 0; inc[k] = 0.0;
+                    if (ok[k]) {
+                        // largest t in [l, h) with G[t] <= x; after the first edge the owner moves forward by at
+                        // most 32 entries (every entry owns >= 1 edge)
+                        u32 h = k == 0 ? cnt : min(cnt, l + WARP + 1);
+                        while (h - l > 1) {
+                            const u32 mid = (l + h) >> 1;
+                            if (sm.G[mid] <= x) l = mid;
+                            else h = mid;
+                        }
+                        const int sj = sm.slot[l];
+                        slot[k] = sj < 0 ? ~sj : sj;
+                        inc[k] = sm.inc[l];
+                        const int32_t* cp = &g.col[sm.beg[l] + (OffT)(x - sm.G[l])];
+                        u[k] = sj < 0 ? sm.source[slot[k]] : (a.l2_hints ? ld_col_stream(cp, pol_stream) : __ldcs(cp));
                     }
                 }
-                const u32 m = __ballot_sync(FULL, cross);
-                if (cross) myq[wq + __popc(m & lanemask_lt())] = ((u64)slot[k] << 32) | (u32)u[k];
-                wq += __popc(m);
+#pragma unroll
+                for (int k = 0; k < PUSH_UB; ++k)
+                    if (ok[k]) {
+                        double* rp = &a.residue[(size_t)slot[k] * a.n + u[k]];
+                        old[k] = a.l2_hints ? atomic_add_f64_hint(rp, inc[k], pol_keep) : atomicAdd(rp, inc[k]);
+                    }
+#pragma unroll
+                for (int k = 0; k < PUSH_UB; ++k) {
+                    bool cross = false;
+                    if (ok[k]) {
+                        // the out-degree is only needed if the add can have crossed rmax*d (d >= 1 => nw >= rmax)
+                        // or was a first touch (a dangling vertex joins on any positive residue)
+                        const double nw = old[k] + inc[k];
+                        const double rm = sm.rmax[slot[k]];
+                        if (nw >= rm || old[k] == 0.0) {
+                            const int32_t du = a.l2_hints ? ld_s32_hint(&a.deg[u[k]], pol_keep) : __ldg(&a.deg[u[k]]);
+                            const double thr = rm * (double)du;
+                            cross = du ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
+                        }
+                    }
+                    // the queue holds one slot at a time; a step rarely spans two (tile at a slot boundary)
+                    u32 pending = __ballot_sync(FULL, cross);
+                    while (pending) {
+                        const int s0 = __shfl_sync(FULL, slot[k], __ffs(pending) - 1);
+                        if (wq && s0 != wq_slot) {
+                            push_flush_warp(a, myq, wq, wq_slot, nxt, nxt_count);
+                            wq = 0;
+                        }
+                        wq_slot = s0;
+                        const u32 m = __ballot_sync(FULL, cross && slot[k] == s0);
+                        if (cross && slot[k] == s0) myq[wq + __popc(m & lanemask_lt())] = ((u64)s0 << 32) | (u32)u[k];
+                        wq += __popc(m);
+                        pending &= ~m;
+                    }
+                }
             }
+            const bool more = sm.G[cnt] < hi && i_cur + cnt < nf;
+            __syncthreads();
+            if (!more) break;
+            i_cur += cnt;
         }
-        const bool more = sm.G[cnt] < hi && i_cur + cnt < nf;
-        __syncthreads();
-        if (!more) break;
-        i_cur += cnt;
     }
-    if (wq) { // final flush of this warp's queue
-        u32 base = 0;
-        __syncwarp();
-        if (lane == 0) base = atomicAdd(nxt_count, wq);
-        base = __shfl_sync(FULL, base, 0);
-        for (u32 t = lane; t < wq; t += WARP) nxt[base + t] = myq[t];
-    }
+    if (wq) push_flush_warp(a, myq, wq, wq_slot, nxt, nxt_count);
 }
 
 template <typename OffT>
@@ -359,19 +427,31 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
     __syncthreads();
 
     for (u32 level = 0;; ++level) {
-        const u32 nf = *((volatile u32*)&ctl->fcount[level % 3]);
+        // the level's frontier: per-slot segments concatenated in slot order
+        if (threadIdx.x == 0) {
+            u32 acc = 0;
+            for (int s = 0; s < a.slots; ++s) {
+                sm.fbase[s] = acc;
+                acc += *((volatile u32*)&ctl->fcount[level % 3][s]);
+            }
+            sm.fbase[a.slots] = acc;
+        }
+        __syncthreads();
+        const u32 nf = sm.fbase[a.slots];
         if (nf == 0 || level >= a.max_levels) break;
         const u64* cur = (level & 1) ? a.front1 : a.front0; // written by the previous level: L2 reads only
         u64* nxt = (level & 1) ? a.front0 : a.front1;
-        u32* nxt_count = &ctl->fcount[(level + 1) % 3];
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            ctl->fcount[(level + 2) % 3] = 0;
-            ctl->levels_run = level + 1;
-            if (a.trace && level < a.trace_cap) {
-                u64 t;
-                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-                a.trace[4 * level] = t;
-                a.trace[4 * level + 1] = nf;
+        u32* nxt_count = ctl->fcount[(level + 1) % 3];
+        if (blockIdx.x == 0) {
+            if (threadIdx.x < (u32)a.slots) ctl->fcount[(level + 2) % 3][threadIdx.x] = 0;
+            if (threadIdx.x == 0) {
+                ctl->levels_run = level + 1;
+                if (a.trace && level < a.trace_cap) {
+                    u64 t;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                    a.trace[4 * level] = t;
+                    a.trace[4 * level + 1] = nf;
+                }
             }
         }
         push_phase_a<OffT>(a, sm, cur, nf, level, blockIdx.x, gridDim.x);
@@ -409,7 +489,10 @@ __global__ void push_init_kernel(int32_t n, int32_t slots, const int32_t* __rest
     } else {
         residue[gi] = 1.0;
         slot_state[slot] = 1;
-        if (seed_source) front0[atomicAdd(&ctl->fcount[0], 1u)] = ((u64)slot << 32) | (u32)s;
+        if (seed_source) {
+            front0[(size_t)slot * n] = ((u64)slot << 32) | (u32)s;
+            ctl->fcount[0][slot] = 1;
+        }
     }
 }
 
@@ -433,7 +516,7 @@ __global__ void __launch_bounds__(256) push_seed_kernel(int32_t n, const int32_t
             const int32_t d = deg[v];
             pred = d ? (r >= rm * (double)d) : (r > 0.0);
         }
-        warp_append<u64>(pred, ((u64)slot << 32) | (u32)v, front0, &ctl->fcount[0]);
+        warp_append<u64>(pred, ((u64)slot << 32) | (u32)v, front0 + (size_t)slot * n, &ctl->fcount[0][slot]);
     }
 }
 

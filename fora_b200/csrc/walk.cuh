@@ -219,20 +219,20 @@ struct WalkArgs {
 };
 
 // The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
-// iteration first stops with probability alpha (skipped once when NO_ZERO_HOP), then moves to a
-// uniform out-neighbour, or back to THIS walk's start when the current vertex is dangling.
-struct Walker {
-    int32_t cur, start;
-    u32 jlo, jhi; // walk index within its source (Philox counter words 0,1)
-    u32 blk;      // Philox draw-block counter (counter word 2)
-    u32 phase;    // 0: draw a new block; 1: second half of the current block
-    Philox4 rnd;
-    bool first;   // forced first hop pending (NO_ZERO_HOP)
-};
-
+// step first stops with probability alpha (skipped once when NO_ZERO_HOP), then moves to a uniform
+// out-neighbour, or back to THIS walk's start when the current vertex is dangling.
+//
+// Per CTA chunk of WALK_CHUNK walks: (1) the prefix of the sources touching the chunk is staged in shared
+// memory, (2) a divergence-free expansion pass resolves the owner source of every walk of the chunk
+// (binary search, all lanes busy), (3) lanes fetch walks dynamically from a shared counter -- a lane that
+// finishes a walk immediately starts the next one, so neither the longest walk of a warp nor the tail of
+// a chunk idles lanes -- and advance two steps per Philox block, so the RNG is evaluated by all lanes in
+// lockstep (one Philox4x32-10 block = stop/pick, stop/pick).
 template <typename OffT, bool NO_ZERO_HOP>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<OffT> g) {
     __shared__ long long s_rel[WALK_CHUNK + 2];
+    __shared__ unsigned short s_own[WALK_CHUNK];
+    __shared__ u32 s_next;
     const int slot = blockIdx.y;
     if (a.slot_state[slot] != 1) return;
     const u64 W = a.nwalk[slot];
@@ -248,75 +248,84 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
 
     for (u64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
         const u64 w0 = chunk * WALK_CHUNK;
-        const u64 w1 = min(W, w0 + (u64)WALK_CHUNK);
+        const u32 nw = (u32)(min(W, w0 + (u64)WALK_CHUNK) - w0);
         const u32 s_lo = cfirst[chunk], s_hi = cfirst[chunk + 1];
         const u32 cnt = s_hi - s_lo + 1; // sources touching this chunk, <= WALK_CHUNK + 1
         __syncthreads();
         for (u32 i = threadIdx.x; i <= cnt; i += WALK_THREADS) s_rel[i] = (long long)woff[s_lo + i] - (long long)w0;
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();
+        // expansion: owner of walk x = last i in [0,cnt) with s_rel[i] <= x
+        for (u32 x = threadIdx.x; x < nw; x += WALK_THREADS) {
+            u32 lo = 0, hi = cnt;
+            while (hi - lo > 1) {
+                const u32 mid = (lo + hi) >> 1;
+                if (s_rel[mid] <= (long long)x) lo = mid;
+                else hi = mid;
+            }
+            s_own[x] = (unsigned short)lo;
+        }
         __syncthreads();
 
-        u64 w = w0 + threadIdx.x;
-        bool need_init = true;
-        Walker wk;
+        int32_t cur = 0, start = 0;
+        u32 jlo = 0, jhi = 0, blk = 0;
         double inc = 0.0;
-        while (w < w1) {
-            if (need_init) {
-                // source of walk w: last i in [0,cnt) with s_rel[i] <= w - w0
-                const long long x = (long long)(w - w0);
-                u32 lo = 0, hi = cnt;
-                while (hi - lo > 1) {
-                    const u32 mid = (lo + hi) >> 1;
-                    if (s_rel[mid] <= x) lo = mid;
-                    else hi = mid;
-                }
-                const u64 j = (u64)(x - s_rel[lo]);
-                const int32_t v = srcs[s_lo + lo];
-                inc = incs[s_lo + lo];
-                wk.cur = wk.start = v;
-                wk.jlo = (u32)j;
-                wk.jhi = (u32)(j >> 32);
-                wk.blk = 0;
-                wk.phase = 0;
-                wk.first = NO_ZERO_HOP;
-                need_init = false;
-                bool done = false;
-                int32_t dest = v;
-                if (a.with_idx) { // query.h:290-307: the first min(n_v, count) walks come from the index
-                    const u64 used = a.idx_used ? a.idx_used[(size_t)slot * a.n + v] : 0;
-                    const u64 have = a.idx_cnt[v] - used;
-                    if (j < have) {
-                        dest = a.idx_dest[a.idx_off[v] + used + j];
-                        done = true;
-                        ++my_hits;
+        bool have = false, first = false;
+        for (;;) {
+            if (!have) { // fetch the next walk of the chunk
+                const u32 x = atomicAdd(&s_next, 1u);
+                if (x < nw) {
+                    const u32 own = s_own[x];
+                    const u64 j = (u64)((long long)x - s_rel[own]);
+                    const int32_t v = srcs[s_lo + own];
+                    inc = incs[s_lo + own];
+                    bool done = false;
+                    int32_t dest = v;
+                    if (a.with_idx) { // query.h:290-307: the first min(n_v, count) walks come from the index
+                        const u64 used = a.idx_used ? a.idx_used[(size_t)slot * a.n + v] : 0;
+                        const u64 avail = a.idx_cnt[v] - used;
+                        if (j < avail) {
+                            dest = a.idx_dest[a.idx_off[v] + used + j];
+                            done = true;
+                            ++my_hits;
+                        }
                     }
+                    if (!done && (u32)(g.ptr[v + 1] - g.ptr[v]) == 0) done = true; // algo.h:127-129
+                    if (done) {
+                        atomicAdd(&ppr[dest], inc);
+                    } else {
+                        cur = start = v;
+                        jlo = (u32)j;
+                        jhi = (u32)(j >> 32);
+                        blk = 0;
+                        first = NO_ZERO_HOP;
+                        have = true;
+                    }
+                } else {
+                    break; // chunk exhausted: this lane waits for its warp-mates at the next barrier
                 }
-                if (!done && (u32)(g.ptr[v + 1] - g.ptr[v]) == 0) done = true; // algo.h:127-129
-                if (done) {
-                    atomicAdd(&ppr[dest], inc);
-                    w += WALK_THREADS;
-                    need_init = true;
-                    continue;
+                if (!have) continue; // resolved without walking (index hit / dangling start): fetch again
+            }
+            // one Philox block = two steps; counter = (walk index lo, hi, block, source)
+            const Philox4 rnd = philox4x32_10(jlo, jhi, blk++, (u32)start, k0, k1);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const u32 r_stop = half ? rnd.z : rnd.x;
+                const u32 r_pick = half ? rnd.w : rnd.y;
+                if (!first && r_stop < a.alpha_thr) { // algo.h:131-133
+                    atomicAdd(&ppr[cur], inc);
+                    have = false;
+                    break;
                 }
-            }
-            // Philox counter = (walk index lo, hi, draw block, source); one block feeds two steps
-            if (wk.phase == 0) wk.rnd = philox4x32_10(wk.jlo, wk.jhi, wk.blk++, (u32)wk.start, k0, k1);
-            const u32 r_stop = wk.phase ? wk.rnd.z : wk.rnd.x;
-            const u32 r_pick = wk.phase ? wk.rnd.w : wk.rnd.y;
-            wk.phase ^= 1u;
-            if (!wk.first && r_stop < a.alpha_thr) { // algo.h:131-133
-                atomicAdd(&ppr[wk.cur], inc);
-                w += WALK_THREADS;
-                need_init = true;
-                continue;
-            }
-            wk.first = false;
-            const OffT b = g.ptr[wk.cur];
-            const u32 d = (u32)(g.ptr[wk.cur + 1] - b);
-            if (d) {
-                wk.cur = __ldg(&g.col[b + (OffT)__umulhi(r_pick, d)]); // algo.h:135-136
-                ++my_hops;
-            } else {
-                wk.cur = wk.start; // algo.h:138-140
+                first = false;
+                const OffT b = g.ptr[cur];
+                const u32 d = (u32)(g.ptr[cur + 1] - b);
+                if (d) {
+                    cur = __ldg(&g.col[b + (OffT)__umulhi(r_pick, d)]); // algo.h:135-136
+                    ++my_hops;
+                } else {
+                    cur = start; // algo.h:138-140
+                }
             }
         }
     }
