@@ -65,14 +65,16 @@ struct DevBuf {
 struct fora_ctx {
     int device = 0;
     uint64_t seed = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_stage_ready = nullptr, ev_stage_free = nullptr;
+    bool stage_busy = false;
     cudaEvent_t ev[8] = {};
     std::string err;
     int num_sms = 0;
     DeviceGraph g;
     fora_params p{};
     bool params_set = false;
-    int slots = 4;
+    int slots = 16;
     int alloc_slots = 0;
     // hot arena: [residue | deg | row offsets (u32) | reserve] in ONE allocation so that an L2 access-policy
     // window can pin the arrays every edge / hop touches at random (B200: 126 MB L2)
@@ -103,6 +105,7 @@ struct fora_ctx {
     DevBuf<u64> woff;
     DevBuf<double> incs;
     DevBuf<u32> chunk_first;
+    DevBuf<double> stage;    // results of a finished wave, copied to the host while the next wave computes
     DevBuf<double> ppr;      // top-k rounds: ppr is rebuilt from reserve every round (query.h:533)
     DevBuf<u64> idx_used;    // top-k with index: per-(slot,vertex) cursor into the index (rw_counter, query.h:575-603)
     size_t chunk_cap = 0;
@@ -202,6 +205,9 @@ extern "C" int fora_ctx_create(int device, uint64_t seed, fora_ctx** out) {
         return FORA_ECUDA;
     }
     ctx->stream = ctx->own_stream;
+    cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_stage_ready, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_stage_free, cudaEventDisableTiming);
     for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     memset(ctx->h_meta, 0, sizeof(SlotMeta));
     ctx->p.alpha = 0.2;
@@ -223,12 +229,15 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     ctx->reserve.release(); ctx->residue.release(); ctx->arena.release(); ctx->front0.release(); ctx->front1.release();
     ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
-    ctx->ppr.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
+    ctx->ppr.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
     ctx->counts.release(); ctx->bwd_res.release(); ctx->bwd_rv.release(); ctx->bwd_lists.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->kev_pool) cudaEventDestroy(ev);
+    if (ctx->ev_stage_ready) cudaEventDestroy(ctx->ev_stage_ready);
+    if (ctx->ev_stage_free) cudaEventDestroy(ctx->ev_stage_free);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -1016,7 +1025,18 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
             CK(cudaMemcpyAsync(ctx->meta.p->nwalk, h->nwalk, sizeof(u64) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
         }
         CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-        if (ppr) CK(cudaMemcpyAsync(ppr + (size_t)q0 * n, ctx->reserve.p, sizeof(double) * n * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ppr) {
+            // results leave through a staging buffer on a second stream, so the device->host copy of wave w
+            // overlaps the computation of wave w+1 (the slot vectors are re-initialised immediately)
+            CK(ctx->stage.ensure(n * (size_t)S));
+            if (ctx->stage_busy) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
+            CK(cudaMemcpyAsync(ctx->stage.p, ctx->reserve.p, sizeof(double) * n * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaEventRecord(ctx->ev_stage_ready, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_ready, 0));
+            CK(cudaMemcpyAsync(ppr + (size_t)q0 * n, ctx->stage.p, sizeof(double) * n * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_stage_free, ctx->copy_stream));
+            ctx->stage_busy = true;
+        }
         CK(cudaEventRecord(ctx->ev[4], ctx->stream));
         if ((rc = meta_d2h_sync(ctx))) return rc;
         if (stats)
@@ -1025,6 +1045,10 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
         CK(cudaEventElapsedTime(&t, ctx->ev[1], ctx->ev[2])); push_ms += t;
         CK(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3])); walk_ms += t;
         CK(cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4])); copy_ms += t;
+    }
+    if (ctx->stage_busy) { // the last copy must have landed before the call returns
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
+        ctx->stage_busy = false;
     }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     CK(cudaEventSynchronize(ctx->ev[5]));
