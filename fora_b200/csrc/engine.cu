@@ -107,6 +107,9 @@ struct fora_ctx {
     DevBuf<u32> chunk_first;
     DevBuf<double> stage;    // results of a finished wave, copied to the host while the next wave computes
     DevBuf<double> ppr;      // top-k rounds: ppr is rebuilt from reserve every round (query.h:533)
+    DevBuf<double> ub, lb;   // non --opt top-k: per-node upper / lower PPR bounds (algo.h:48-49)
+    DevBuf<unsigned char> in_topk;
+    DevBuf<u32> flags;
     DevBuf<u64> idx_used;    // top-k with index: per-(slot,vertex) cursor into the index (rw_counter, query.h:575-603)
     size_t chunk_cap = 0;
     // index
@@ -229,7 +232,7 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     ctx->reserve.release(); ctx->residue.release(); ctx->arena.release(); ctx->front0.release(); ctx->front1.release();
     ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
-    ctx->ppr.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
+    ctx->ppr.release(); ctx->ub.release(); ctx->lb.release(); ctx->in_topk.release(); ctx->flags.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
     ctx->counts.release(); ctx->bwd_res.release(); ctx->bwd_rv.release(); ctx->bwd_lists.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
@@ -1109,10 +1112,11 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
     auto restore = [&](int code) { ctx->p = keep; return code; };
     const double min_delta = 1.0 / n;
     if (algo == FORA_ALGO_FORA) {
-        if (!keep.opt) return ctx->fail(FORA_EINVAL, "top-k without --opt (fora_query_topk_with_bound, query.h:909) is not implemented yet");
-        // fora_query_topk_new (query.h:972-1045): pfail = 1/n^2; the largest omega is reached at delta = 1/n
+        // the largest omega of either driver is reached at delta = 1/n with its own pfail
+        // (fora_query_topk_new: 1/n^2, query.h:977; fora_query_topk_with_bound: 1/n^2/ln n, query.h:915)
         double rm, om;
-        fora_host_setting(1, n, ctx->g.m_decl, keep.epsilon, min_delta, 1.0 / n / n, keep.alpha, keep.opt, keep.rmax_scale, &rm, &om);
+        fora_host_setting(keep.opt ? 1 : 0, n, ctx->g.m_decl, keep.epsilon, min_delta, keep.opt ? 1.0 / n / n : 1.0 / n / n / log((double)n), keep.alpha,
+                          keep.opt, keep.rmax_scale, &rm, &om);
         if ((rc = require_ready(ctx, om))) return rc;
     } else if ((rc = require_ready(ctx, keep.omega))) return rc;
     const int S = ctx->slots;
@@ -1136,7 +1140,110 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
         const double* result = ctx->reserve.p; // where each slot's final vector lives
         std::vector<int32_t> it(cnt, 0);
         std::vector<u64> tot_walks(cnt, 0), tot_hits(cnt, 0), tot_hops(cnt, 0);
-        if (algo == FORA_ALGO_FORA) {
+        if (algo == FORA_ALGO_FORA && !keep.opt) {
+            // ---- fora_query_topk_with_bound (query.h:909-969): delta from 1/4 halving, per-node bounds, if_stop ----
+            CK(ctx->ppr.ensure(nn * S));
+            CK(ctx->ub.ensure(nn * S));
+            CK(ctx->lb.ensure(nn * S));
+            CK(ctx->in_topk.ensure(nn));
+            CK(ctx->flags.ensure(4));
+            const bool use_idx = keep.with_idx && ctx->has_index;
+            if (use_idx) {
+                CK(ctx->idx_used.ensure(nn * S));
+                CK(cudaMemsetAsync(ctx->idx_used.p, 0, sizeof(u64) * nn * cnt, ctx->stream)); // query.h:935-936
+            }
+            if ((rc = init_wave(ctx, cnt, 0, nullptr))) return restore(rc);
+            if ((rc = meta_d2h_sync(ctx))) return restore(rc);
+            std::vector<char> done(cnt, 0);
+            for (int s = 0; s < cnt; ++s) {
+                done[s] = h->state[s] != 1;
+                if (h->state[s] == 2) it[s] = 1;
+            }
+            fill_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->ub.p, nn * cnt, 1.0); // upper_bounds.reset_one_values(), query.h:940
+            CKL();
+            CK(cudaMemsetAsync(ctx->lb.p, 0, sizeof(double) * nn * cnt, ctx->stream));          // lower_bounds.reset_zero_values()
+            CK(cudaMemsetAsync(ctx->in_topk.p, 0, nn, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->ppr.p, ctx->reserve.p, sizeof(double) * nn * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+            const double pfail = 1.0 / n / n / log((double)n);                               // query.h:915
+            const double threshold = (1.0 - 0.77) / pow(500, 0.77) / pow((double)n, 1 - 0.77); // query.h:913, ppr_decay_alpha = 0.77
+            double delta = 1.0 / 4;                                                           // query.h:912
+            for (int round = 0; round < 64 && delta >= min_delta; ++round) {
+                bool any = false;
+                double rmax, omega;
+                fora_host_setting(0, n, ctx->g.m_decl, keep.epsilon, delta, pfail, keep.alpha, 0, keep.rmax_scale, &rmax, &omega); // fora_setting, query.h:944
+                for (int s = 0; s < MAX_SLOTS; ++s) h->active[s] = 0;
+                for (int s = 0; s < cnt; ++s)
+                    if (!done[s]) { h->active[s] = 1; h->rmax[s] = rmax; any = true; it[s]++; }
+                if (!any) break;
+                if ((rc = push_round_active(ctx))) return restore(rc);
+                for (int s = 0; s < cnt; ++s) h->state[s] = done[s] ? (h->state[s] == 1 ? 3 : h->state[s]) : 1;
+                CK(cudaMemcpyAsync(ctx->meta.p->state, h->state, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+                for (int s = 0; s < cnt; ++s)
+                    if (!done[s]) CK(cudaMemcpyAsync(ctx->ppr.p + nn * s, ctx->reserve.p + nn * s, sizeof(double) * nn, cudaMemcpyDeviceToDevice, ctx->stream));
+                ctx->p.omega = omega;
+                ctx->p.rmax = rmax;
+                // walks: plain random_walk, n_v = ceil(r/rsum*N) (no index, query.h:724-740) or ceil(r*omega) (index, 656-662)
+                if ((rc = walk_wave(ctx, ctx->ppr.p, use_idx ? 3 : 0, 0, 0, (u32)(round + 1), use_idx ? ctx->idx_used.p : nullptr))) return restore(rc);
+                if (use_idx) {
+                    idx_cursor_kernel<<<dim3(ctx->num_sms * 2, S), 256, 0, ctx->stream>>>(n, ctx->srcs.p, ctx->woff.p, ctx->meta.p->nsrc, ctx->idx_cnt.p, ctx->idx_used.p, ctx->meta.p->state);
+                    CKL();
+                }
+                if ((rc = meta_d2h_sync(ctx))) return restore(rc);
+                CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+                for (int s = 0; s < cnt; ++s) {
+                    if (done[s]) continue;
+                    tot_walks[s] += h->nwalk[s]; tot_hits[s] += h->idx_hits[s]; tot_hops[s] += h->hops[s];
+                    const double rsum_s = h->rsum[s];
+                    const double real_rw = (double)h->nwalk[s];
+                    if (delta < threshold && real_rw > 0 && rsum_s > 0) { // set_ppr_bounds, query.h:745-746
+                        ppr_bounds_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, rsum_s, pfail, real_rw, ctx->ppr.p + nn * s, ctx->reserve.p + nn * s,
+                                                                                   ctx->ub.p + nn * s, ctx->lb.p + nn * s);
+                        CKL();
+                    }
+                    // if_stop(), algo.h:1096-1166
+                    bool stop = false;
+                    double kth = 0.0;
+                    cudaError_t e = topk_device(ctx->stream, ctx->num_sms, ctx->ppr.p + nn * s, n, k, nullptr, nullptr, &ctx->launches, &kth);
+                    if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("kth select: ") + cudaGetErrorString(e)));
+                    if (kth >= 2.0 * delta) stop = true;
+                    else if (!(delta >= threshold)) {
+                        int32_t* d_nodes = nullptr;
+                        u32 got = 0;
+                        double low_k = 0.0;
+                        e = topk_device(ctx->stream, ctx->num_sms, ctx->lb.p + nn * s, n, k, nullptr, nullptr, &ctx->launches, &low_k, &d_nodes, &got);
+                        if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("bound select: ") + cudaGetErrorString(e)));
+                        // fewer than k positive lower bounds: some top-k node has lower bound 0 => ratio test fails (algo.h:1129-1134)
+                        if (got == k && low_k > delta) {
+                            CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(u32) * 4, ctx->stream));
+                            stop_mark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->ub.p + nn * s, ctx->lb.p + nn * s, keep.epsilon, ctx->in_topk.p, ctx->flags.p);
+                            stop_tail_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, ctx->ppr.p + nn * s, ctx->ub.p + nn * s, ctx->lb.p + nn * s, ctx->in_topk.p, low_k,
+                                                                                      keep.epsilon, ctx->flags.p);
+                            stop_unmark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->in_topk.p);
+                            ctx->launches += 3;
+                            u32 hf[2];
+                            CK(cudaMemcpyAsync(hf, ctx->flags.p, sizeof(u32) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+                            CK(cudaStreamSynchronize(ctx->stream));
+                            stop = !hf[0] && !hf[1];
+                        }
+                    }
+                    if (stop || delta <= min_delta) done[s] = 1; // query.h:963
+                }
+                CK(cudaEventRecord(ctx->ev[7], ctx->stream));
+                CK(cudaEventSynchronize(ctx->ev[7]));
+                float t;
+                CK(cudaEventElapsedTime(&t, ctx->ev[6], ctx->ev[7]));
+                topk_ms += t;
+                CK(cudaMemsetAsync(ctx->meta.p->hops, 0, sizeof(u64) * MAX_SLOTS, ctx->stream));
+                CK(cudaMemsetAsync(ctx->meta.p->idx_hits, 0, sizeof(u64) * MAX_SLOTS, ctx->stream));
+                delta = std::max(min_delta, delta / 2.0); // query.h:966
+                bool all = true;
+                for (int s = 0; s < cnt; ++s) all = all && done[s];
+                if (all) break;
+            }
+            result = ctx->ppr.p;
+            for (int s = 0; s < cnt; ++s) { fr[s] = ctx->p.rmax; rounds[s] = (u64)it[s]; }
+            ctx->p = keep;
+        } else if (algo == FORA_ALGO_FORA) {
             CK(ctx->ppr.ensure(nn * S));
             const bool use_idx = keep.with_idx && ctx->has_index;
             if (use_idx) {

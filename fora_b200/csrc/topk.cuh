@@ -168,7 +168,8 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(int32_t* nodes, double*
 
 // Select + sort on the device, results copied to host arrays of length k.
 static inline cudaError_t topk_device(cudaStream_t stream, int num_sms, const double* d_vals, int32_t n, u32 k,
-                                      int32_t* h_nodes, double* h_values, u64* launches, double* kth_value = nullptr) {
+                                      int32_t* h_nodes, double* h_values, u64* launches, double* kth_value = nullptr,
+                                      int32_t** d_nodes_out = nullptr, u32* count_out = nullptr, bool sort_on_device = false) {
     static thread_local SelectState* d_st = nullptr;
     static thread_local int32_t* d_nodes = nullptr;
     static thread_local double* d_out = nullptr;
@@ -203,6 +204,14 @@ static inline cudaError_t topk_device(cudaStream_t stream, int num_sms, const do
     if ((e = cudaMemcpyAsync(&hs, d_st, sizeof(SelectState), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
     const u32 cnt = std::min<u32>(hs.out_count, k);
+    if (d_nodes_out) *d_nodes_out = d_nodes;
+    if (count_out) *count_out = cnt;
+    if (sort_on_device && cnt > 0 && !(h_nodes && h_values)) {
+        u32 c2 = 1;
+        while (c2 < cnt) c2 <<= 1;
+        topk_sort_kernel<<<1, 1024, 0, stream>>>(d_nodes, d_out, cnt, c2);
+        *launches += 1;
+    }
     if (kth_value) {
         double t = 0.0;
         if (!hs.all_positive) memcpy(&t, &hs.key_T, sizeof t);
@@ -267,6 +276,87 @@ static inline cudaError_t power_iteration_device(cudaStream_t stream, int num_sm
         if ((e = cudaMemsetAsync(nxt, 0, sizeof(double) * (size_t)n, stream)) != cudaSuccess) return e;
     }
     return cudaGetLastError();
+}
+
+} // namespace fora
+
+// =============================================================================================
+// Bounds of the non --opt top-k driver: set_ppr_bounds (/root/reference/algo.h:1178-1261),
+// calculate_lambda (algo.h:1169-1174) and the tail test of if_stop (algo.h:1147-1163).
+// =============================================================================================
+namespace fora {
+
+__host__ __device__ inline double calculate_lambda(double rsum, double pfail, double upper_bound, double total_rw_num) {
+    return 1.0 / 3 * log(2 / pfail) * rsum / total_rw_num +
+           sqrt(4.0 / 9.0 * log(2.0 / pfail) * log(2.0 / pfail) * rsum * rsum + 8 * total_rw_num * log(2.0 / pfail) * rsum * upper_bound) / 2.0 /
+               total_rw_num;
+}
+
+// one thread per vertex of one slot; bounds start at upper = 1, lower = 0 (query.h:940-941)
+__global__ void __launch_bounds__(256) ppr_bounds_kernel(int32_t n, double rsum, double pfail, double total_rw_num,
+                                                          const double* __restrict__ ppr, const double* __restrict__ reserve,
+                                                          double* __restrict__ upper, double* __restrict__ lower) {
+    const double min_ppr = 1.0 / n, sqrt_min_ppr = sqrt(1.0 / n);
+    const double epsilon_v_div = sqrt(2.67 * rsum * log(2.0 / pfail) / total_rw_num);
+    const double default_epsilon_v = epsilon_v_div / sqrt_min_ppr;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        const double p = ppr[v];
+        if (p <= 0) continue;
+        double res = reserve[v]; // 0 when absent
+        double epsilon_a;
+        if (upper[v] > res) epsilon_a = calculate_lambda(rsum, pfail, upper[v] - res, total_rw_num);
+        else epsilon_a = calculate_lambda(rsum, pfail, 1 - res, total_rw_num);
+        const double ub_eps_a = p + epsilon_a;
+        double lb_eps_a = p - epsilon_a;
+        if (!(lb_eps_a > 0)) lb_eps_a = 0;
+        double epsilon_v = default_epsilon_v;
+        if (res > min_ppr) {
+            res = fmax(res, lower[v]);
+            epsilon_v = epsilon_v_div / sqrt(res);
+        } else if (lower[v] > 0) {
+            epsilon_v = epsilon_v_div / sqrt(lower[v]);
+        }
+        double ub_eps_v = 1.0, lb_eps_v = 0.0;
+        if (1.0 - epsilon_v > 0) {
+            ub_eps_v = p / (1.0 - epsilon_v);
+            lb_eps_v = p / (1.0 + epsilon_v);
+        }
+        const double up_bound = fmin(fmin(ub_eps_a, ub_eps_v), 1.0);
+        const double low_bound = fmax(fmax(lb_eps_a, lb_eps_v), res);
+        if (up_bound > 0) upper[v] = up_bound;
+        if (low_bound >= 0) lower[v] = low_bound;
+    }
+}
+
+__global__ void fill_kernel(double* p, size_t n, double v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// if_stop part 2 (algo.h:1124-1163) given the k nodes with the largest lower bounds:
+//   fail[0] |= any of them has upper/lower > 1+eps;   in_topk marks them
+__global__ void stop_mark_kernel(const int32_t* __restrict__ nodes, u32 k, const double* __restrict__ upper,
+                                 const double* __restrict__ lower, double eps, unsigned char* __restrict__ in_topk, u32* fail) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
+        const int32_t v = nodes[i];
+        in_topk[v] = 1;
+        if (upper[v] / lower[v] > 1.0 + eps) atomicOr(fail, 1u);
+    }
+}
+//   fail[1] |= a node outside the top-k with ppr > 0 whose upper bound exceeds low_bound_k*(1+eps) without being
+//   separated by (1+eps)/(1-eps)
+__global__ void __launch_bounds__(256) stop_tail_kernel(int32_t n, const double* __restrict__ ppr, const double* __restrict__ upper,
+                                                         const double* __restrict__ lower, const unsigned char* __restrict__ in_topk,
+                                                         double low_bound_k, double eps, u32* fail) {
+    bool bad = false;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        if (in_topk[v] || ppr[v] <= 0) continue;
+        const double u = upper[v], l = lower[v];
+        if (u > low_bound_k * (1.0 + eps) && !(u > (1 + eps) / (1 - eps) * l)) bad = true;
+    }
+    if (__any_sync(FULL, bad) && lane_id() == 0) atomicOr(fail + 1, 1u);
+}
+__global__ void stop_unmark_kernel(const int32_t* __restrict__ nodes, u32 k, unsigned char* __restrict__ in_topk) {
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) in_topk[nodes[i]] = 0;
 }
 
 } // namespace fora

@@ -26,7 +26,7 @@ struct PlanArgs {
     int32_t n;
     double alpha, omega;
     int opt;        // --opt: rsum *= (1-alpha), ppr[v] += alpha*r, r *= (1-alpha)  (query.h:349,363-364)
-    int per_round;  // top-k rounds: n_v = ceil(r*omega), inc = (r*omega/n_v)/omega     (query.h:568-571)
+    int per_round;  // top-k rounds: 1: n_v = ceil(r*omega), inc = (r*omega/n_v)/omega (query.h:568-571); 3: the with-bound/index hybrid
     const double* __restrict__ residue; // [slots*n]
     double* ppr;                        // [slots*n] in/out: holds reserve on entry (may alias reserve)
     const double* __restrict__ rsum;    // [slots]
@@ -45,6 +45,12 @@ struct PlanArgs {
 // n_v and inc_v for one source; identical expression order to query.h:314-317 (and 349,400-404).
 __device__ __forceinline__ void plan_one(const PlanArgs& a, double r, double check_rsum, u64 num_random_walk, u64* n_v,
                                          double* inc) {
+    if (a.per_round == 3) { // compute_ppr_with_fwdidx_topk_with_bound with index, query.h:659-662
+        *n_v = (u64)ceil(__dmul_rn(r, a.omega));
+        const double a_s = __ddiv_rn(__dmul_rn(__ddiv_rn(r, check_rsum), (double)num_random_walk), (double)*n_v);
+        *inc = __ddiv_rn(__dmul_rn(a_s, check_rsum), (double)num_random_walk);
+        return;
+    }
     if (a.per_round) { // query.h:567-571
         const double num = ceil(__dmul_rn(r, a.omega));
         *n_v = (u64)num;

@@ -435,6 +435,37 @@ def test_topk_batch_fora_opt(with_idx):
     E.close()
 
 
+def test_topk_batch_fora_with_bound():
+    # fora_query_topk_with_bound (query.h:909-969) + set_ppr_bounds / if_stop (algo.h:1096-1261): non --opt top-k
+    g2 = Graph.synth(6000, 72000, seed=13)
+    k = 50
+    E = fb.Engine(0, seed=4, slots=4)
+    E.upload_graph(g2.n, g2.m_decl, g2.out_ptr, g2.out_col)
+    E.configure("fora", EPS, opt=0, k=k)
+    srcs = np.array([21, 5, 300, int(np.flatnonzero(g2.deg == 0)[0]), 77], np.int32)
+    nodes, vals, iters, stats, tm = E.topk_batch("fora", srcs, k)
+    O = Oracle(g2, seed=8)
+    O.set_params(EPS, 0.0, 0.0, opt=0, k=k)
+    O.init_state(-9.0, 1)
+    pg, po, itg, ito = [], [], [], []
+    for i, s in enumerate(srcs):
+        if g2.deg[s] == 0:
+            assert nodes[i][0] == s and vals[i][0] == 1.0
+            continue
+        exact = O.power_iteration(int(s), 150)
+        top = set(np.argsort(-exact, kind="stable")[:k].tolist())
+        pg.append(len(set(nodes[i].tolist()) & top) / k)
+        O.reset_counters()
+        O.fora_topk_with_bound(int(s), 0)
+        on, ov = O.topk_ppr(k)
+        po.append(len(set(on.tolist()) & top) / k)
+        itg.append(int(iters[i])); ito.append(O.counters()["topk_iters"])
+        assert (np.diff(vals[i]) <= 0).all()
+    assert np.mean(pg) > 0.9 and abs(np.mean(pg) - np.mean(po)) < 0.05, (pg, po)
+    assert abs(np.mean(itg) - np.mean(ito)) <= 2.0, (itg, ito)  # same stopping rule => similar number of rounds
+    E.close()
+
+
 def test_topk_batch_baselines(g, eng):
     k = 30
     O = Oracle(g)
