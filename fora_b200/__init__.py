@@ -96,6 +96,12 @@ def lib():
     L.fora_query_batch_device.argtypes = [vp, C.c_int, vp, C.c_int32, C.POINTER(QueryStat), C.POINTER(BatchTiming)]
     L.fora_device_ppr.restype = vp
     L.fora_device_ppr.argtypes = [vp, C.c_int]
+    L.fora_prepare_slots.argtypes = [vp]
+    L.fora_device_reserve.restype = vp
+    L.fora_device_reserve.argtypes = [vp, C.c_int]
+    L.fora_device_residue.restype = vp
+    L.fora_device_residue.argtypes = [vp, C.c_int]
+    L.fora_compute_ppr_part_device.argtypes = [vp, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(QueryStat)]
     L.fora_topk_batch.argtypes = [vp, C.c_int, c_ip, C.c_int32, C.c_uint32, c_ip, c_dp, c_ip, C.POINTER(QueryStat), C.POINTER(BatchTiming)]
     L.fora_topk_of.argtypes = [vp, c_dp, C.c_uint32, c_ip, c_dp]
     L.fora_index_info.argtypes = [vp, c_up, c_up, c_up]
@@ -289,6 +295,20 @@ class Engine:
         tm = BatchTiming()
         self._ck(self.L.fora_query_batch_device(self.h, ALGO[algo], C.c_void_p(d_sources_ptr), nq, stats, C.byref(tm)))
         return [stats[i].as_dict() for i in range(nq)], tm.as_dict()
+
+    def prepare_slots(self):
+        self._ck(self.L.fora_prepare_slots(self.h))
+
+    def device_reserve_ptr(self, slot=0):
+        return self.L.fora_device_reserve(self.h, slot)
+
+    def device_residue_ptr(self, slot=0):
+        return self.L.fora_device_residue(self.h, slot)
+
+    def compute_ppr_part_device(self, rsum, qid, part, nparts):
+        st = QueryStat()
+        self._ck(self.L.fora_compute_ppr_part_device(self.h, rsum, qid, part, nparts, C.byref(st)))
+        return st.as_dict()
 
     def device_ppr_ptr(self, slot):
         return self.L.fora_device_ppr(self.h, slot)

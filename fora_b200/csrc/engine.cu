@@ -653,7 +653,8 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
 
 // Walk phase of a wave: plan + walk kernels; ppr is accumulated in place into `ppr` ([slots*n],
 // holding the reserve on entry).  round_tag distinguishes the Philox streams of top-k rounds.
-static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_zero_hop, u32 round_tag, const u64* idx_used) {
+static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_zero_hop, u32 round_tag, const u64* idx_used,
+                     u32 part = 0, u32 nparts = 1) {
     const DeviceGraph& g = ctx->g;
     const int S = ctx->slots;
     SlotMeta* m = ctx->meta.p;
@@ -663,6 +664,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     pa.blk_src = ctx->blk_src.p; pa.blk_walk = ctx->blk_walk.p; pa.srcs = ctx->srcs.p; pa.woff = ctx->woff.p;
     pa.incs = ctx->incs.p; pa.nsrc = m->nsrc; pa.nwalk = m->nwalk;
     pa.nblk = (g.n + PLAN_THREADS - 1) / PLAN_THREADS;
+    pa.no_credit = part > 0;
     plan_kernel<false><<<dim3(pa.nblk, S), PLAN_THREADS, 0, ctx->stream>>>(pa);
     CKL();
     plan_scan_kernel<<<S, 1024, 0, ctx->stream>>>(pa);
@@ -679,6 +681,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.with_idx = ctx->p.with_idx && ctx->has_index;
     wa.srcs = ctx->srcs.p; wa.woff = ctx->woff.p; wa.incs = ctx->incs.p; wa.nsrc = m->nsrc; wa.nwalk = m->nwalk;
     wa.chunk_first = ctx->chunk_first.p; wa.chunk_cap = ctx->chunk_cap; wa.slot_state = m->state; wa.qid = m->qid;
+    wa.part = part; wa.nparts = nparts;
     wa.round_tag = round_tag; wa.ppr = ppr; wa.hops = m->hops; wa.idx_hits = m->idx_hits;
     wa.idx_off = ctx->idx_off.p; wa.idx_cnt = ctx->idx_cnt.p; wa.idx_dest = ctx->idx_dest.p; wa.idx_used = idx_used;
     const int wgx = ctx->num_sms * 8;
@@ -944,6 +947,44 @@ static int bippr_one(fora_ctx* ctx, int32_t source, u32 qid, double* d_ppr, u64*
     CK(cudaStreamSynchronize(ctx->stream));
     if (ovf) return ctx->fail(FORA_ECUDA, "backward push: touched list overflow");
     *n_walks = nw; *hops = h2[0]; *edges = h2[1];
+    return FORA_OK;
+}
+
+
+// =============================================================================================
+// multi-GPU split of ONE query (Twitter-scale): every GPU holds the same push state
+// (broadcast by the caller into fora_device_reserve / fora_device_residue of slot 0), walks its share of the
+// walk chunks into its own dense vector and the caller sums the vectors (ncclAllReduce over NVLink).
+// part 0 starts from the reserve (+ alpha*r credit with --opt), the other parts from zero.
+// =============================================================================================
+extern "C" void* fora_device_reserve(fora_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= ctx->alloc_slots) return nullptr;
+    return ctx->reserve.p + (size_t)ctx->g.n * slot;
+}
+extern "C" void* fora_device_residue(fora_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot >= ctx->alloc_slots) return nullptr;
+    return ctx->residue.p + (size_t)ctx->g.n * slot;
+}
+extern "C" int fora_prepare_slots(fora_ctx* ctx) { return require_ready(ctx, ctx ? ctx->p.omega : 0); }
+
+extern "C" int fora_compute_ppr_part_device(fora_ctx* ctx, double rsum, uint32_t qid, uint32_t part, uint32_t nparts, fora_query_stat* stat) {
+    int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
+    if (rc) return rc;
+    if (nparts == 0 || part >= nparts) return ctx->fail(FORA_EINVAL, "bad part / nparts");
+    const size_t n = (size_t)ctx->g.n;
+    SlotMeta* h = ctx->h_meta;
+    memset(h, 0, sizeof *h);
+    for (int s = 0; s < MAX_SLOTS; ++s) h->source[s] = -1;
+    h->source[0] = 0;
+    h->qid[0] = qid;
+    h->state[0] = rsum == 0.0 ? 2 : 1;
+    h->rsum[0] = rsum;
+    if ((rc = meta_h2d(ctx))) return rc;
+    if (part > 0) CK(cudaMemsetAsync(ctx->reserve.p, 0, sizeof(double) * n, ctx->stream));
+    if ((rc = walk_wave(ctx, ctx->reserve.p, 0, ctx->p.opt, ctx->p.opt, 0, nullptr, part, nparts))) return rc;
+    if ((rc = meta_d2h_sync(ctx))) return rc;
+    if (stat) fill_stat(ctx, 0, ctx->p.rmax, 0, stat);
+    ctx->session_source = -1;
     return FORA_OK;
 }
 

@@ -40,6 +40,7 @@ struct PlanArgs {
     u64* __restrict__ nsrc;      // [slots]
     u64* __restrict__ nwalk;     // [slots]
     int nblk;
+    int no_credit; // multi-GPU walk split: parts > 0 start from a zero vector and skip the alpha*r credit
 };
 
 // n_v and inc_v for one source; identical expression order to query.h:314-317 (and 349,400-404).
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(PlanArgs a) {
         a.srcs[(size_t)slot * a.n + pos] = v;
         a.woff[(size_t)slot * (a.n + 1) + pos] = wo;
         a.incs[(size_t)slot * a.n + pos] = inc;
-        if (a.opt || a.per_round == 2) a.ppr[gi] += __dmul_rn(r, a.alpha); // query.h:363 / 562
+        if ((a.opt || a.per_round == 2) && !a.no_credit) a.ppr[gi] += __dmul_rn(r, a.alpha); // query.h:363 / 562
     }
 }
 
@@ -222,6 +223,7 @@ struct WalkArgs {
     const u64* __restrict__ idx_cnt;
     const int32_t* __restrict__ idx_dest;
     const u64* __restrict__ idx_used; // per-round cursor (top-k), may be null
+    u32 part, nparts;                 // multi-GPU walk split: this launch walks chunks [part*C/nparts, (part+1)*C/nparts)
 };
 
 // The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
@@ -252,7 +254,9 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
     const u32 k0 = a.seed_lo ^ (a.qid[slot] * 0x9E3779B9u), k1 = a.seed_hi ^ a.round_tag;
     u64 my_hops = 0, my_hits = 0;
 
-    for (u64 chunk = blockIdx.x; chunk < nchunks; chunk += gridDim.x) {
+    const u64 chunk_lo = a.nparts > 1 ? nchunks * a.part / a.nparts : 0;
+    const u64 chunk_hi = a.nparts > 1 ? nchunks * (a.part + 1) / a.nparts : nchunks;
+    for (u64 chunk = chunk_lo + blockIdx.x; chunk < chunk_hi; chunk += gridDim.x) {
         const u64 w0 = chunk * WALK_CHUNK;
         const u32 nw = (u32)(min(W, w0 + (u64)WALK_CHUNK) - w0);
         const u32 s_lo = cfirst[chunk], s_hi = cfirst[chunk + 1];

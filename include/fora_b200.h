@@ -155,6 +155,18 @@ int fora_query_batch_device(fora_ctx* ctx, int algo, const int32_t* d_sources, i
 /* device pointer (double[n]) of the PPR vector of slot `slot` after the last batch */
 void* fora_device_ppr(fora_ctx* ctx, int slot);
 
+/* ---- one query split over several GPUs (whole-graph SSPPR at Twitter scale) ----
+ * The reference computes `ppr = reserve + sum of walk increments` on one core (query.h:255-413); here every
+ * GPU receives the same push state (device pointers of slot 0 below, filled e.g. by an NCCL broadcast), walks
+ * chunk range `part` of `nparts` of the SAME walk plan (Philox keys do not depend on the split) into its own dense
+ * vector, and the caller reduces the vectors (ncclAllReduce / torch.distributed over NVLink).  part 0 starts from
+ * the reserve, the others from zero, so the sum equals the single-GPU result up to fp64 summation order. */
+int fora_prepare_slots(fora_ctx* ctx); /* allocate the per-slot state so the pointers below exist */
+void* fora_device_reserve(fora_ctx* ctx, int slot); /* device double[n] */
+void* fora_device_residue(fora_ctx* ctx, int slot); /* device double[n] */
+int fora_compute_ppr_part_device(fora_ctx* ctx, double rsum, uint32_t query_id, uint32_t part, uint32_t nparts,
+                                 fora_query_stat* stat); /* result in fora_device_reserve(ctx, 0) */
+
 /* get_topk(), query.h:1139-1190: k (node,value) pairs per query, descending, unfilled = (0,0.0)
  * (algo.h:592-610).  iters: per-query refinement rounds (num_iter_topk) or NULL. */
 int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, uint32_t k, int32_t* nodes,
