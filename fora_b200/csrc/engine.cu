@@ -33,6 +33,8 @@ struct SlotMeta {
     int32_t lastlvl[MAX_SLOTS];
     double rsum[MAX_SLOTS];
     u64 nnz[MAX_SLOTS], nsrc[MAX_SLOTS], nwalk[MAX_SLOTS], hops[MAX_SLOTS], idx_hits[MAX_SLOTS];
+    double next_rmax[MAX_SLOTS]; // speculative seeding threshold of the following round (0: none)
+    u32 seed_count[MAX_SLOTS];   // seeds found for it (segments of front0)
 };
 
 template <typename T>
@@ -548,9 +550,16 @@ static int launch_push(fora_ctx* ctx) {
     return FORA_OK;
 }
 
-static int launch_residue_stats(fora_ctx* ctx) {
+// rsum / nnz of every slot; with seed_next also the seed lists of the next round at h_meta->next_rmax
+static int launch_residue_stats(fora_ctx* ctx, bool seed_next = false) {
     const int S = ctx->slots;
-    residue_partial_kernel<<<dim3(ctx->red_blocks, S), RED_THREADS, 0, ctx->stream>>>(ctx->g.n, ctx->residue.p, ctx->part_sum.p, ctx->part_nnz.p);
+    SlotMeta* m = ctx->meta.p;
+    if (seed_next) {
+        CK(cudaMemcpyAsync(m->next_rmax, ctx->h_meta->next_rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(m->seed_count, 0, sizeof(u32) * MAX_SLOTS, ctx->stream));
+    }
+    residue_partial_kernel<<<dim3(ctx->red_blocks, S), RED_THREADS, 0, ctx->stream>>>(ctx->g.n, ctx->residue.p, ctx->part_sum.p, ctx->part_nnz.p, ctx->hot_deg,
+                                                                                     seed_next ? m->next_rmax : nullptr, ctx->front0.p, m->seed_count);
     CKL();
     residue_final_kernel<<<S, 32, 0, ctx->stream>>>(ctx->red_blocks, ctx->part_sum.p, ctx->part_nnz.p, ctx->meta.p->rsum, ctx->meta.p->nnz);
     CKL();
@@ -581,17 +590,27 @@ static int init_wave(fora_ctx* ctx, int cnt, int seed_source, const int32_t* d_s
 }
 
 // one resumable round over the slots flagged in h_meta->active (rmax per slot in h_meta->rmax)
-static int push_round_active(fora_ctx* ctx) {
-    CK(cudaMemcpyAsync(ctx->meta.p->rmax, ctx->h_meta->rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->meta.p->active, ctx->h_meta->active, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+// have_seeds: the previous stats pass already produced this round's seed lists (h_meta->seed_count, front0);
+// next_seed: let this round's stats pass prepare the following round at h_meta->next_rmax
+static int push_round_active(fora_ctx* ctx, bool have_seeds = false, bool next_seed = false) {
+    SlotMeta* h = ctx->h_meta;
+    CK(cudaMemcpyAsync(ctx->meta.p->rmax, h->rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->meta.p->active, h->active, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
-    const int gx = std::max(1, std::min(ctx->num_sms * 8, (ctx->g.n + 255) / 256));
-    push_seed_kernel<<<dim3(gx, ctx->slots), 256, 0, ctx->stream>>>(ctx->g.n, ctx->hot_deg, ctx->residue.p, ctx->meta.p->rmax,
-                                                                   ctx->meta.p->active, ctx->front0.p, ctx->ctl.p);
-    CKL();
+    if (have_seeds) {
+        u32 cnt[MAX_SLOTS];
+        for (int s = 0; s < MAX_SLOTS; ++s) cnt[s] = h->active[s] ? h->seed_count[s] : 0; // slots that stopped keep their residue
+        CK(cudaMemcpyAsync(ctx->ctl.p->fcount[0], cnt, sizeof(cnt), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream)); // cnt lives on this stack frame
+    } else {
+        const int gx = std::max(1, std::min(ctx->num_sms * 8, (ctx->g.n + 255) / 256));
+        push_seed_kernel<<<dim3(gx, ctx->slots), 256, 0, ctx->stream>>>(ctx->g.n, ctx->hot_deg, ctx->residue.p, ctx->meta.p->rmax,
+                                                                       ctx->meta.p->active, ctx->front0.p, ctx->ctl.p);
+        CKL();
+    }
     int rc = launch_push(ctx);
     if (rc) return rc;
-    return launch_residue_stats(ctx);
+    return launch_residue_stats(ctx, next_seed);
 }
 
 // Push phase of a wave of `cnt` FORA queries: plain (algo.h:954) or --balanced (query.h:848-884).
@@ -635,7 +654,9 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
             any = true;
         }
         if (!any) break;
-        if ((rc = push_round_active(ctx))) return rc;
+        // the stats pass of this round also lists the seeds of the next one (rmax/2) for every active slot
+        for (int s = 0; s < MAX_SLOTS; ++s) h->next_rmax[s] = (s < cnt && h->active[s]) ? rmax[s] / 2 : 0.0;
+        if ((rc = push_round_active(ctx, iter > 0, true))) return rc;
         if ((rc = meta_d2h_sync(ctx))) return rc;
         for (int s = 0; s < cnt; ++s) {
             if (!h->active[s]) continue;

@@ -525,21 +525,37 @@ __global__ void __launch_bounds__(256) push_seed_kernel(int32_t n, const int32_t
 // number of non-zero entries.  grid = (blocks, slots).
 // ---------------------------------------------------------------------------------------------
 constexpr int RED_THREADS = 256;
+// The same dense pass also prepares the NEXT resumable round speculatively: every vertex with
+// residue >= next_rmax*d_out (dangling: any positive residue) is appended to the slot's seed segment, so a
+// round that does continue starts without a second scan of the residue vectors.
 __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n, const double* __restrict__ residue,
                                                                       double* __restrict__ part_sum,
-                                                                      u32* __restrict__ part_nnz) {
+                                                                      u32* __restrict__ part_nnz,
+                                                                      const int32_t* __restrict__ deg,
+                                                                      const double* __restrict__ next_rmax, // [slots], <= 0: no seeding
+                                                                      u64* __restrict__ seeds, u32* __restrict__ seed_count) {
     __shared__ double s_sum[RED_THREADS];
     __shared__ u32 s_nnz[RED_THREADS];
     const int slot = blockIdx.y;
     const double* __restrict__ res = residue + (size_t)slot * n;
-    const int per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int per_block = (((n + gridDim.x - 1) / gridDim.x) + WARP - 1) / WARP * WARP;
     const int lo = blockIdx.x * per_block, hi = min(n, lo + per_block);
+    const double rm = next_rmax ? next_rmax[slot] : 0.0;
     double s = 0.0;
     u32 c = 0;
-    for (int v = lo + threadIdx.x; v < hi; v += RED_THREADS) {
-        const double r = res[v];
-        s += r;
-        c += r > 0.0;
+    for (int v0 = lo; v0 < hi; v0 += RED_THREADS) { // warp-uniform trip count (per_block is a multiple of 32)
+        const int v = v0 + threadIdx.x;
+        bool seed = false;
+        if (v < hi) {
+            const double r = res[v];
+            s += r;
+            c += r > 0.0;
+            if (rm > 0.0 && r > 0.0) {
+                const int32_t d = deg[v];
+                seed = d ? (r >= rm * (double)d) : true;
+            }
+        }
+        if (rm > 0.0 && v0 + (int)(threadIdx.x & ~31u) < hi) warp_append<u64>(seed, ((u64)slot << 32) | (u32)v, seeds + (size_t)slot * n, &seed_count[slot]);
     }
     s_sum[threadIdx.x] = s;
     s_nnz[threadIdx.x] = c;
