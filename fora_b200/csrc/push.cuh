@@ -26,7 +26,7 @@ namespace cg = cooperative_groups;
 
 constexpr int PUSH_THREADS = 512;
 constexpr int PUSH_WARPS = PUSH_THREADS / WARP;
-constexpr int MAX_SLOTS = 64;
+constexpr int MAX_SLOTS = 64; // also bounded by the 8 slot bits of a frontier entry
 constexpr int MAX_PUSH_CTAS = 512;
 constexpr u32 TILE_MIN = 2048;   // smallest edge range worth giving to a CTA
 constexpr u32 TILE_MAX = 16384;  // tiles of a large level: the grid sweeps the edge line 296*16K edges at a time
@@ -34,6 +34,16 @@ constexpr int PUSH_UA = 4;       // frontier entries per thread per phase-A batc
 constexpr int PUSH_BATCH = 1024; // frontier entries staged in shared memory per phase-B batch
 constexpr int PUSH_UB = 4;       // edges in flight per lane in phase B
 constexpr int PUSH_WQ = 256;     // per-warp queue of crossing vertices
+
+// frontier entry: [slot:8][min(out-degree, 2^24-1):24][vertex:32].  Whoever appends a vertex has just loaded its
+// out-degree for the threshold test, so carrying it saves phase A one random access per vertex.
+constexpr u32 DEG_SAT = 0xffffffu;
+__host__ __device__ __forceinline__ u64 make_entry(int slot, u32 deg, int32_t v) {
+    return ((u64)(u32)slot << 56) | ((u64)(deg < DEG_SAT ? deg : DEG_SAT) << 32) | (u32)v;
+}
+__host__ __device__ __forceinline__ int entry_slot(u64 e) { return (int)(e >> 56); }
+__host__ __device__ __forceinline__ u32 entry_deg24(u64 e) { return (u32)(e >> 32) & DEG_SAT; }
+__host__ __device__ __forceinline__ int32_t entry_vertex(u64 e) { return (int32_t)(u32)e; }
 
 struct PushCtl {
     u32 fcount[3][MAX_SLOTS]; // per-slot frontier sizes, rotated by level % 3
@@ -48,7 +58,7 @@ struct PushArgs {
     double* reserve;  // [slots*n]   (mutated across levels: no __restrict__, read with __ldcg)
     double* residue;  // [slots*n]
     const int32_t* __restrict__ deg;
-    u64* front0;      // [slots*n]: slot s owns [s*n, (s+1)*n); entries (slot<<32 | v)
+    u64* front0;      // [slots*n]: slot s owns [s*n, (s+1)*n); entries make_entry(slot, deg, v)
     u64* front1;
     double* inc;      // per frontier entry (global index): ((1-alpha)*r)/d, or (1-alpha)*r when dangling
     u32* eoff;        // per frontier entry: edge offset inside its CTA chunk
@@ -84,6 +94,7 @@ struct PushSmem {
     u32 cnt_edges[MAX_SLOTS], cnt_verts[MAX_SLOTS];
     u32 fbase[MAX_SLOTS + 1];    // the level's frontier = the slots' segments concatenated in slot order
     u32 i0;
+    u32 step_ctr;                // dynamic hand-out of 32*PUSH_UB-edge steps inside a batch
 };
 
 
@@ -170,10 +181,11 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             r[k] = rs[k] = 0.0;
             d[k] = 0;
             if (e[k] != ~0ull) {
-                const size_t gi = (size_t)(e[k] >> 32) * a.n + (u32)e[k];
+                const size_t gi = (size_t)entry_slot(e[k]) * a.n + (u32)e[k];
                 r[k] = __ldcg(&a.residue[gi]);
                 rs[k] = __ldcg(&a.reserve[gi]);
-                d[k] = (u32)__ldg(&a.deg[(u32)e[k]]);
+                d[k] = entry_deg24(e[k]);
+                if (d[k] == DEG_SAT) d[k] = (u32)__ldg(&a.deg[(u32)e[k]]);
             }
         }
         u32 esum = 0, vcnt = 0, dsum = 0;
@@ -182,7 +194,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
 #pragma unroll
         for (int k = 0; k < PUSH_UA; ++k) {
             if (e[k] == ~0ull) continue;
-            const int slot = (int)(e[k] >> 32);
+            const int slot = entry_slot(e[k]);
             const size_t gi = (size_t)slot * a.n + (u32)e[k];
             a.residue[gi] = 0.0;
             a.reserve[gi] = rs[k] + r[k] * a.alpha;
@@ -206,8 +218,8 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
 #pragma unroll
             for (int k = 0; k < PUSH_UA; ++k)
                 if (e[k] != ~0ull) {
-                    atomicAdd(&sm.cnt_edges[(int)(e[k] >> 32)], d[k]);
-                    atomicAdd(&sm.cnt_verts[(int)(e[k] >> 32)], 1u);
+                    atomicAdd(&sm.cnt_edges[entry_slot(e[k])], d[k]);
+                    atomicAdd(&sm.cnt_verts[entry_slot(e[k])], 1u);
                 }
         }
         u64 total;
@@ -321,22 +333,26 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
                 const u32 i = i_cur + t;
                 if (t < cnt) {
                     const u64 e = frontier_entry(a, sm, cur, i);
-                    const int slot = (int)(e >> 32);
-                    const int32_t v = (int32_t)(u32)e;
+                    const int slot = entry_slot(e);
+                    const int32_t v = entry_vertex(e);
                     const OffT beg = g.ptr[v];
-                    const bool dang = g.ptr[v + 1] == beg;
+                    const bool dang = entry_deg24(e) == 0;
                     sm.G[t] = sm.base[i / cs] + __ldcg(&a.eoff[i]);
                     sm.beg[t] = beg;
                     sm.inc[t] = __ldcg(&a.inc[i]);
                     sm.slot[t] = dang ? ~slot : slot;
                 } else {
                     sm.G[cnt] = i < nf ? sm.base[i / cs] + __ldcg(&a.eoff[i]) : E;
+                    sm.step_ctr = PUSH_WARPS; // steps 0..PUSH_WARPS-1 are pre-assigned, one per warp
                 }
             }
             __syncthreads();
             const u64 x_lo = max(lo, sm.G[0]), x_hi = min(hi, sm.G[cnt]);
-            // warp w takes steps w, w + PUSH_WARPS, ... of 32*PUSH_UB consecutive edges
-            for (u64 xb = x_lo + (u64)w * (WARP * PUSH_UB); xb < x_hi; xb += (u64)PUSH_WARPS * WARP * PUSH_UB) {
+            // warp w starts with step w, further steps are handed out dynamically (no warp waits at the batch barrier
+            // for a neighbour that drew one more step)
+            for (u64 step = w;; ) {
+                const u64 xb = x_lo + step * (u64)(WARP * PUSH_UB);
+                if (xb >= x_hi) break;
                 if (wq > PUSH_WQ - WARP * PUSH_UB) { // make room: one global atomic per flush
                     push_flush_warp(a, myq, wq, wq_slot, nxt, nxt_count);
                     wq = 0;
@@ -367,25 +383,25 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
                         u[k] = sj < 0 ? sm.source[slot[k]] : (a.l2_hints ? ld_col_stream(cp, pol_stream) : __ldcs(cp));
                     }
                 }
+                // the out-degrees of the targets are fetched alongside the atomics (both depend only on the
+                // column values), so a step is two dependent memory round trips instead of three
+                int32_t du[PUSH_UB];
 #pragma unroll
-                for (int k = 0; k < PUSH_UB; ++k)
+                for (int k = 0; k < PUSH_UB; ++k) {
+                    du[k] = 0;
                     if (ok[k]) {
                         double* rp = &a.residue[(size_t)slot[k] * a.n + u[k]];
                         old[k] = a.l2_hints ? atomic_add_f64_hint(rp, inc[k], pol_keep) : atomicAdd(rp, inc[k]);
+                        du[k] = a.l2_hints ? ld_s32_hint(&a.deg[u[k]], pol_keep) : __ldg(&a.deg[u[k]]);
                     }
+                }
 #pragma unroll
                 for (int k = 0; k < PUSH_UB; ++k) {
                     bool cross = false;
                     if (ok[k]) {
-                        // the out-degree is only needed if the add can have crossed rmax*d (d >= 1 => nw >= rmax)
-                        // or was a first touch (a dangling vertex joins on any positive residue)
                         const double nw = old[k] + inc[k];
-                        const double rm = sm.rmax[slot[k]];
-                        if (nw >= rm || old[k] == 0.0) {
-                            const int32_t du = a.l2_hints ? ld_s32_hint(&a.deg[u[k]], pol_keep) : __ldg(&a.deg[u[k]]);
-                            const double thr = rm * (double)du;
-                            cross = du ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
-                        }
+                        const double thr = sm.rmax[slot[k]] * (double)du[k];
+                        cross = du[k] ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
                     }
                     // the queue holds one slot at a time; a step rarely spans two (tile at a slot boundary)
                     u32 pending = __ballot_sync(FULL, cross);
@@ -397,11 +413,14 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
                         }
                         wq_slot = s0;
                         const u32 m = __ballot_sync(FULL, cross && slot[k] == s0);
-                        if (cross && slot[k] == s0) myq[wq + __popc(m & lanemask_lt())] = ((u64)s0 << 32) | (u32)u[k];
+                        if (cross && slot[k] == s0) myq[wq + __popc(m & lanemask_lt())] = make_entry(s0, (u32)du[k], u[k]);
                         wq += __popc(m);
                         pending &= ~m;
                     }
                 }
+                u32 nxt_step = 0;
+                if (lane == 0) nxt_step = atomicAdd(&sm.step_ctr, 1u);
+                step = __shfl_sync(FULL, nxt_step, 0);
             }
             const bool more = sm.G[cnt] < hi && i_cur + cnt < nf;
             __syncthreads();
@@ -490,7 +509,7 @@ __global__ void push_init_kernel(int32_t n, int32_t slots, const int32_t* __rest
         residue[gi] = 1.0;
         slot_state[slot] = 1;
         if (seed_source) {
-            front0[(size_t)slot * n] = ((u64)slot << 32) | (u32)s;
+            front0[(size_t)slot * n] = make_entry(slot, (u32)deg[s], s);
             ctl->fcount[0][slot] = 1;
         }
     }
@@ -511,12 +530,15 @@ __global__ void __launch_bounds__(256) push_seed_kernel(int32_t n, const int32_t
     for (int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < nwarp_iters; wi += (gridDim.x * blockDim.x) >> 5) {
         const int v = wi * WARP + lane_id();
         bool pred = false;
+        int32_t d = 0;
         if (v < n) {
             const double r = res[v];
-            const int32_t d = deg[v];
-            pred = d ? (r >= rm * (double)d) : (r > 0.0);
+            if (r > 0.0) {
+                d = deg[v];
+                pred = d ? (r >= rm * (double)d) : true;
+            }
         }
-        warp_append<u64>(pred, ((u64)slot << 32) | (u32)v, front0 + (size_t)slot * n, &ctl->fcount[0][slot]);
+        warp_append<u64>(pred, make_entry(slot, (u32)d, v), front0 + (size_t)slot * n, &ctl->fcount[0][slot]);
     }
 }
 
@@ -546,16 +568,17 @@ __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n,
     for (int v0 = lo; v0 < hi; v0 += RED_THREADS) { // warp-uniform trip count (per_block is a multiple of 32)
         const int v = v0 + threadIdx.x;
         bool seed = false;
+        int32_t d = 0;
         if (v < hi) {
             const double r = res[v];
             s += r;
             c += r > 0.0;
             if (rm > 0.0 && r > 0.0) {
-                const int32_t d = deg[v];
+                d = deg[v];
                 seed = d ? (r >= rm * (double)d) : true;
             }
         }
-        if (rm > 0.0 && v0 + (int)(threadIdx.x & ~31u) < hi) warp_append<u64>(seed, ((u64)slot << 32) | (u32)v, seeds + (size_t)slot * n, &seed_count[slot]);
+        if (rm > 0.0 && v0 + (int)(threadIdx.x & ~31u) < hi) warp_append<u64>(seed, make_entry(slot, (u32)d, v), seeds + (size_t)slot * n, &seed_count[slot]);
     }
     s_sum[threadIdx.x] = s;
     s_nnz[threadIdx.x] = c;
