@@ -81,6 +81,7 @@ def lib():
     L.fora_ctx_set_slots.argtypes = [vp, C.c_int]
     L.fora_ctx_sync.argtypes = [vp]
     L.fora_graph_upload.argtypes = [vp, C.c_int32, C.c_int64, c_lp, c_ip, c_lp, c_ip]
+    L.fora_graph_build_from_edges.argtypes = [vp, C.c_int32, C.c_int64, c_ip, c_ip, C.c_int64, C.c_int]
     L.fora_graph_download_csr.argtypes = [vp, c_lp, c_ip, c_lp, c_ip]
     L.fora_graph_num_edges.restype = C.c_int64
     L.fora_graph_num_edges.argtypes = [vp]
@@ -218,6 +219,13 @@ class Engine:
             in_ptr = np.ascontiguousarray(in_ptr, np.int64)
             in_col = np.ascontiguousarray(in_col, np.int32)
         self._ck(self.L.fora_graph_upload(self.h, n, m_decl, _p(out_ptr, c_lp), _p(out_col, c_ip), _p(in_ptr, c_lp), _p(in_col, c_ip)))
+        self.n, self.m_decl = n, m_decl
+
+    def build_graph_from_edges(self, n, m_decl, src, dst, with_in=True):
+        """K0: CSR built on the device from the edge list in file order"""
+        src = np.ascontiguousarray(src, np.int32)
+        dst = np.ascontiguousarray(dst, np.int32)
+        self._ck(self.L.fora_graph_build_from_edges(self.h, n, m_decl, _p(src, c_ip), _p(dst, c_ip), len(src), int(with_in)))
         self.n, self.m_decl = n, m_decl
 
     def download_csr(self, with_in=True):

@@ -12,6 +12,10 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+
 #include "bippr.cuh"
 #include "common.cuh"
 #include "push.cuh"
@@ -337,6 +341,122 @@ extern "C" int fora_graph_download_csr(fora_ctx* ctx, int64_t* out_ptr, int32_t*
     return FORA_OK;
 }
 extern "C" int64_t fora_graph_num_edges(fora_ctx* ctx) { return ctx ? ctx->g.n_edges : FORA_EINVAL; }
+
+
+// =============================================================================================
+// K0: CSR construction on the device from an edge list in file order (Graph::init_graph, graph.h:152-160):
+// drop self loops, keep duplicates, keep file order inside every adjacency list.  "File order inside a list" is
+// exactly a STABLE sort of the edges by source (out-CSR) / by target (in-CSR), so the build is: flag + stable
+// compaction, stable LSD radix sort of (key, value) pairs, histogram + exclusive scan for the row offsets.
+// The sort / scan / select primitives are CUB's (the CUDA toolkit's library, like calling cuBLAS for a GEMM):
+// this is load-time plumbing, not the query hot path.
+// =============================================================================================
+__global__ void k0_flag_kernel(int64_t ne, const int32_t* __restrict__ src, const int32_t* __restrict__ dst, int32_t n,
+                               unsigned char* __restrict__ keep, int* __restrict__ bad) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t s = src[e], d = dst[e];
+        if ((u32)s >= (u32)n || (u32)d >= (u32)n) *bad = 1; // graph.h:155-156
+        keep[e] = s != d;                                    // graph.h:157
+    }
+}
+__global__ void k0_count_kernel(int64_t ne, const int32_t* __restrict__ key, unsigned long long* __restrict__ cnt) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[key[e]], 1ull);
+}
+
+static int k0_one_direction(fora_ctx* ctx, int32_t n, int64_t kept, const int32_t* d_key, const int32_t* d_val, int64_t* d_ptr,
+                            int32_t* d_col, int key_bits) {
+    DevBuf<int32_t> key_out;
+    DevBuf<unsigned long long> cnt;
+    DevBuf<unsigned char> tmp;
+    CK(key_out.ensure((size_t)std::max<int64_t>(kept, 1)));
+    CK(cnt.ensure((size_t)n + 1));
+    CK(cudaMemsetAsync(cnt.p, 0, sizeof(unsigned long long) * ((size_t)n + 1), ctx->stream));
+    if (kept > 0) {
+        k0_count_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(kept, d_key, cnt.p);
+        CKL();
+        size_t bytes = 0;
+        CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, d_key, key_out.p, d_val, d_col, kept, 0, key_bits, ctx->stream));
+        CK(tmp.ensure(bytes));
+        CK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, d_key, key_out.p, d_val, d_col, kept, 0, key_bits, ctx->stream)); // stable
+    }
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, (unsigned long long*)d_ptr, n + 1, ctx->stream));
+    CK(tmp.ensure(bytes));
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, cnt.p, (unsigned long long*)d_ptr, n + 1, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    key_out.release(); cnt.release(); tmp.release();
+    return FORA_OK;
+}
+
+extern "C" int fora_graph_build_from_edges(fora_ctx* ctx, int32_t n, int64_t m_decl, const int32_t* src, const int32_t* dst,
+                                           int64_t n_edges, int with_in) {
+    if (!ctx) return FORA_EINVAL;
+    if (n <= 0 || n_edges < 0 || (n_edges && (!src || !dst))) return ctx->fail(FORA_EINVAL, "graph_build_from_edges: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const size_t ne = (size_t)n_edges;
+    DevBuf<int32_t> d_src, d_dst, k_src, k_dst;
+    DevBuf<unsigned char> keep, tmp;
+    DevBuf<int> flags;
+    CK(d_src.ensure(std::max<size_t>(ne, 1))); CK(d_dst.ensure(std::max<size_t>(ne, 1)));
+    CK(k_src.ensure(std::max<size_t>(ne, 1))); CK(k_dst.ensure(std::max<size_t>(ne, 1)));
+    CK(keep.ensure(std::max<size_t>(ne, 1))); CK(flags.ensure(4));
+    CK(cudaMemcpyAsync(d_src.p, src, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_dst.p, dst, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(flags.p, 0, sizeof(int) * 4, ctx->stream));
+    int64_t kept = 0;
+    if (ne) {
+        k0_flag_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n_edges, d_src.p, d_dst.p, n, keep.p, flags.p);
+        CKL();
+        size_t bytes = 0;
+        CK(cub::DeviceSelect::Flagged(nullptr, bytes, d_src.p, keep.p, k_src.p, flags.p + 1, n_edges, ctx->stream));
+        CK(tmp.ensure(bytes));
+        CK(cub::DeviceSelect::Flagged(tmp.p, bytes, d_src.p, keep.p, k_src.p, flags.p + 1, n_edges, ctx->stream)); // order preserving
+        CK(cub::DeviceSelect::Flagged(tmp.p, bytes, d_dst.p, keep.p, k_dst.p, flags.p + 2, n_edges, ctx->stream));
+        int hf[4];
+        CK(cudaMemcpyAsync(hf, flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (hf[0]) return ctx->fail(FORA_ERANGE, "edge list contains a node id >= n (graph.h:155-156)");
+        kept = hf[1];
+    }
+    free_graph(ctx->g);
+    DeviceGraph& g = ctx->g;
+    g.n = n; g.m_decl = m_decl; g.n_edges = kept;
+    g.off32 = kept < (int64_t)0xffffffffLL;
+    int key_bits = 1;
+    while ((1ll << key_bits) < (long long)n) ++key_bits;
+    CK(cudaMalloc((void**)&g.out_ptr64, sizeof(int64_t) * ((size_t)n + 1)));
+    CK(cudaMalloc((void**)&g.out_col, sizeof(int32_t) * std::max<size_t>((size_t)kept, 1)));
+    CK(cudaMalloc((void**)&g.deg, sizeof(int32_t) * (size_t)n));
+    if (g.off32) CK(cudaMalloc((void**)&g.out_ptr32, sizeof(u32) * ((size_t)n + 1)));
+    int rc = k0_one_direction(ctx, n, kept, k_src.p, k_dst.p, g.out_ptr64, g.out_col, key_bits);
+    if (rc) return rc;
+    degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.out_ptr64, g.deg, g.out_ptr32);
+    CKL();
+    if (with_in) {
+        CK(cudaMalloc((void**)&g.in_ptr64, sizeof(int64_t) * ((size_t)n + 1)));
+        CK(cudaMalloc((void**)&g.in_col, sizeof(int32_t) * std::max<size_t>((size_t)kept, 1)));
+        if (g.off32) CK(cudaMalloc((void**)&g.in_ptr32, sizeof(u32) * ((size_t)n + 1)));
+        if ((rc = k0_one_direction(ctx, n, kept, k_dst.p, k_src.p, g.in_ptr64, g.in_col, key_bits))) return rc;
+        if (g.off32) {
+            DevBuf<int32_t> t2;
+            CK(t2.ensure((size_t)n));
+            degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.in_ptr64, t2.p, g.in_ptr32);
+            CKL();
+            CK(cudaStreamSynchronize(ctx->stream));
+            t2.release();
+        }
+        g.has_in = true;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    d_src.release(); d_dst.release(); k_src.release(); k_dst.release(); keep.release(); tmp.release(); flags.release();
+    ctx->alloc_slots = 0;
+    ctx->has_index = false;
+    ctx->session_source = -1;
+    ctx->bwd_blocks = 0;
+    return FORA_OK;
+}
 
 // =============================================================================================
 // parameters

@@ -34,41 +34,116 @@ int fora_host_read_attribute(const char* path, int32_t* n, int64_t* m) {
     return FORA_OK;
 }
 
-// Whitespace-separated decimal pairs, as fscanf("%d%d") reads them (graph.h:154); the whole file is
-// read once and scanned by hand (the reference's fscanf loop dominates load time at 1e9 edges).
+// Whitespace-separated decimal pairs, as fscanf("%d%d") reads them (graph.h:154): tokens pair up in sequence,
+// line structure is irrelevant.  The reference's fscanf loop dominates load time at 1e9 edges, so the file is
+// mapped once and scanned by all host cores: chunks are cut at whitespace, pass 1 counts the tokens of every chunk
+// (which fixes the pairing parity at each chunk start), pass 2 parses the pairs of every chunk in parallel and the
+// pieces are concatenated in file order (a pair straddling a chunk boundary is stitched in the merge).
+namespace {
+struct ChunkOut {
+    std::vector<int32_t> src, dst;
+    long long lead = 0, last = 0; // first token when the chunk starts mid-pair / dangling last token
+    bool has_lead = false, has_last = false, bad = false;
+};
+inline bool is_digit(char c) { return c >= '0' && c <= '9'; }
+size_t count_tokens(const char* p, const char* e) {
+    size_t c = 0;
+    bool in = false;
+    for (; p < e; ++p) {
+        const bool d = is_digit(*p) || *p == '-';
+        c += d && !in;
+        in = d;
+    }
+    return c;
+}
+void parse_chunk(const char* p, const char* e, bool odd_start, int32_t n, bool store, ChunkOut& out) {
+    long long val = 0, first = 0;
+    bool in = false, neg = false, have_first = false;
+    bool lead_pending = odd_start;
+    auto token = [&](long long v) {
+        if (lead_pending) { out.lead = v; out.has_lead = true; lead_pending = false; return; }
+        if (!have_first) { first = v; have_first = true; return; }
+        have_first = false;
+        if (!(first < n) || !(v < n)) { out.bad = true; return; } // graph.h:155-156
+        if (first == v) return;                                    // graph.h:157
+        if (store) { out.src.push_back((int32_t)first); out.dst.push_back((int32_t)v); }
+        else out.src.push_back(0); // count only
+    };
+    for (; p < e; ++p) {
+        const char ch = *p;
+        if (is_digit(ch)) { val = val * 10 + (ch - '0'); in = true; }
+        else if (ch == '-' && !in) neg = true;
+        else {
+            if (in) token(neg ? -val : val);
+            val = 0; in = false; neg = false;
+        }
+    }
+    if (in) token(neg ? -val : val);
+    if (have_first) { out.last = first; out.has_last = true; }
+}
+} // namespace
+
 int64_t fora_host_read_edges(const char* path, int32_t n, int32_t* src, int32_t* dst) {
     FILE* f = fopen(path, "rb");
     if (!f) return FORA_EIO;
-    const size_t BUF = 1 << 24;
-    std::vector<char> buf(BUF);
+    fseek(f, 0, SEEK_END);
+    const long long size = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf((size_t)size + 1);
+    if (size > 0 && fread(buf.data(), 1, (size_t)size, f) != (size_t)size) { fclose(f); return FORA_EIO; }
+    fclose(f);
+    buf[(size_t)size] = '\n';
+    const char* base = buf.data();
+    unsigned T = std::thread::hardware_concurrency();
+    if (T == 0) T = 1;
+    if ((long long)T * (1 << 16) > size) T = (unsigned)std::max<long long>(1, size >> 16);
+    std::vector<size_t> cut(T + 1, (size_t)size);
+    cut[0] = 0;
+    for (unsigned t = 1; t < T; ++t) {
+        size_t c = (size_t)(size * (long long)t / T);
+        while (c < (size_t)size && (is_digit(base[c]) || base[c] == '-')) ++c; // never cut inside a token
+        cut[t] = std::max(c, cut[t - 1]);
+    }
+    std::vector<size_t> ntok(T, 0);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t) th.emplace_back([&, t] { ntok[t] = count_tokens(base + cut[t], base + cut[t + 1]); });
+        for (auto& x : th) x.join();
+    }
+    std::vector<char> odd(T, 0);
+    size_t acc = 0;
+    for (unsigned t = 0; t < T; ++t) { odd[t] = (char)(acc & 1); acc += ntok[t]; }
+    std::vector<ChunkOut> out(T);
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; ++t)
+            th.emplace_back([&, t] { parse_chunk(base + cut[t], base + cut[t + 1], odd[t] != 0, n, src != nullptr, out[t]); });
+        for (auto& x : th) x.join();
+    }
     int64_t kept = 0;
-    long long val = 0;
-    bool in_num = false, neg = false, have_first = false;
-    long long first = 0;
-    size_t got;
-    auto flush = [&](long long v) -> int {
-        if (!have_first) { first = v; have_first = true; return 0; }
-        have_first = false;
-        if (!(first < n) || !(v < n)) return 1; // graph.h:155-156
-        if (first == v) return 0;                // graph.h:157
-        if (src) { src[kept] = (int32_t)first; dst[kept] = (int32_t)v; }
-        ++kept;
-        return 0;
-    };
     bool bad = false;
-    while (!bad && (got = fread(buf.data(), 1, BUF, f)) > 0) {
-        for (size_t i = 0; i < got; ++i) {
-            const char ch = buf[i];
-            if (ch >= '0' && ch <= '9') { val = val * 10 + (ch - '0'); in_num = true; }
-            else if (ch == '-' && !in_num) { neg = true; }
-            else {
-                if (in_num) { if (flush(neg ? -val : val)) { bad = true; break; } }
-                val = 0; in_num = false; neg = false;
+    long long pend = 0;
+    bool have_pend = false;
+    for (unsigned t = 0; t < T; ++t) {
+        bad = bad || out[t].bad;
+        if (out[t].has_lead) { // second half of a pair that started in an earlier chunk
+            if (have_pend) {
+                if (!(pend < n) || !(out[t].lead < n)) bad = true;
+                else if (pend != out[t].lead) {
+                    if (src) { src[kept] = (int32_t)pend; dst[kept] = (int32_t)out[t].lead; }
+                    ++kept;
+                }
+                have_pend = false;
             }
         }
+        const size_t c = out[t].src.size();
+        if (src && c) {
+            memcpy(src + kept, out[t].src.data(), c * sizeof(int32_t));
+            memcpy(dst + kept, out[t].dst.data(), c * sizeof(int32_t));
+        }
+        kept += (int64_t)c;
+        if (out[t].has_last) { pend = out[t].last; have_pend = true; }
     }
-    if (!bad && in_num && flush(neg ? -val : val)) bad = true;
-    fclose(f);
     return bad ? (int64_t)FORA_ERANGE : kept;
 }
 

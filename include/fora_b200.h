@@ -74,6 +74,10 @@ int fora_ctx_sync(fora_ctx* ctx);
  * m_decl is attribute.txt's m (used by every formula even when self loops were dropped). */
 int fora_graph_upload(fora_ctx* ctx, int32_t n, int64_t m_decl, const int64_t* out_ptr, const int32_t* out_col,
                       const int64_t* in_ptr, const int32_t* in_col);
+/* The same construction on the device, from the edge list in file order (graph.h:152-160: self loops dropped,
+ * duplicates and file order kept == stable sort by source / by target).  src/dst host int32[n_edges]. */
+int fora_graph_build_from_edges(fora_ctx* ctx, int32_t n, int64_t m_decl, const int32_t* src, const int32_t* dst,
+                                int64_t n_edges, int with_in);
 int fora_graph_download_csr(fora_ctx* ctx, int64_t* out_ptr, int32_t* out_col, int64_t* in_ptr, int32_t* in_col);
 int64_t fora_graph_num_edges(fora_ctx* ctx);
 

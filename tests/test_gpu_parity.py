@@ -59,6 +59,30 @@ def test_csr_roundtrip_bit_exact(gold):
     E.close()
 
 
+def test_device_csr_build_bit_exact(gold, g):
+    # K0: count -> scan -> stable fill on the device == the reference's push_back order (graph.h:152-160)
+    n = int(gold["n"])
+    E = fb.Engine(0)
+    E.build_graph_from_edges(n, int(gold["m_decl"]), gold["src"], gold["dst"])
+    op, oc, ip_, ic = E.download_csr()
+    assert np.array_equal(op, gold["out_ptr"]) and np.array_equal(oc, gold["out_col"])
+    assert np.array_equal(ip_, gold["in_ptr"]) and np.array_equal(ic, gold["in_col"])
+    g3 = Graph.synth(30000, 400000, seed=9, self_loops=50)
+    E.build_graph_from_edges(g3.n, g3.m_decl, g3.src, g3.dst)
+    op, oc, ip_, ic = E.download_csr()
+    assert np.array_equal(op, g3.out_ptr) and np.array_equal(oc, g3.out_col) and np.array_equal(ip_, g3.in_ptr) and np.array_equal(ic, g3.in_col)
+    # and the engine runs on it
+    rmax, _ = E.configure("fora", EPS)
+    res, rsd, rsum, _ = E.push_only(3, rmax)
+    assert abs(res.sum() + rsd.sum() - 1) < 1e-12
+    with pytest.raises(fb.ForaError):
+        E.build_graph_from_edges(10, 3, np.array([1, 2, 10], np.int32), np.array([2, 3, 1], np.int32))  # id >= n
+    E.build_graph_from_edges(5, 0, np.empty(0, np.int32), np.empty(0, np.int32))  # empty edge list
+    op, oc, ip_, ic = E.download_csr()
+    assert op.tolist() == [0] * 6 and len(oc) == 0
+    E.close()
+
+
 # ------------------------------------------------------------------------------------ push
 def test_push_matches_schedule_matched_oracle(g, eng):
     rmax, omega = eng.configure("fora", EPS)

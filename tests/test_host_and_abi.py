@@ -111,3 +111,27 @@ def test_synthetic_generator_is_deterministic_and_shaped():
     # the C ABI CSR equals the numpy restatement used to feed the oracle
     g = Graph(20000, a[0], a[1])
     assert np.array_equal(op, g.out_ptr) and np.array_equal(oc, g.out_col) and np.array_equal(ip_, g.in_ptr) and np.array_equal(ic, g.in_col)
+
+
+def test_parallel_loader_matches_sequential_semantics():
+    # many chunks (the loader cuts the file per 64 KB per thread), pairs straddling chunk boundaries, ragged whitespace
+    rng = np.random.default_rng(5)
+    n, ne = 50000, 400000
+    src = rng.integers(0, n, ne)
+    dst = rng.integers(0, n, ne)
+    dst[::97] = src[::97]  # self loops
+    seps = np.array([" ", "\t", "\n", "  ", " \n", "\r\n"])
+    toks = np.empty(2 * ne, dtype=object)
+    toks[0::2] = src.astype(str)
+    toks[1::2] = dst.astype(str)
+    sp = seps[rng.integers(0, len(seps), 2 * ne)]
+    text = "".join(t + s for t, s in zip(toks, sp))
+    d = tempfile.mkdtemp()
+    path = os.path.join(d, "graph.txt")
+    open(path, "w").write(text)
+    s2, d2 = fb.read_edges(path, n)
+    keep = src != dst
+    assert np.array_equal(s2, src[keep]) and np.array_equal(d2, dst[keep])
+    open(path, "w").write(text + " 7")  # dangling last token: fscanf stops, the pair is never formed
+    s3, d3 = fb.read_edges(path, n)
+    assert np.array_equal(s3, s2) and np.array_equal(d3, d2)
