@@ -40,7 +40,7 @@ struct Config {
     bool multithread = false, with_rw_idx = false, opt = false, balanced = false, force_rebuild = false;
     double omega = 0, rmax = 0, pfail = 0, epsilon = 0, delta = 0, rmax_scale = 1, rw_cost_ratio = 8.0, alpha = 0.2;
     unsigned query_size = 1000, k = 500, hub_space_consum = 1;
-    int gpus = 1, slots = 1;
+    int gpus = 1, slots = 16;
     uint64_t seed = 0;
     string get_graph_folder() const { return prefix + graph_alias + "/"; }
 };
@@ -49,8 +49,7 @@ static Config config;
 struct GraphHost {
     int32_t n = 0;
     int64_t m = 0;
-    vector<int64_t> out_ptr, in_ptr;
-    vector<int32_t> out_col, in_col;
+    vector<int32_t> src, dst; // edge list in file order (self loops already dropped); the CSR is built on the device
 };
 
 static bool exists_test(const string& name) {
@@ -76,8 +75,8 @@ static void die(const string& msg, int code = 1) {
         if (rc__) die(string("fora_b200: ") + #call + ": " + fora_last_error(ctx), 1);     \
     } while (0)
 
-// Graph graph(folder): graph.h:37-46,89-163
-static GraphHost load_graph(const string& folder, bool need_edges, bool need_in) {
+// Graph graph(folder): graph.h:37-46,89-163 -- the text is parsed on all host cores, the adjacency (CSR) is built on the GPU
+static GraphHost load_graph(const string& folder, bool need_edges) {
     GraphHost g;
     const string attr = folder + "attribute.txt";
     if (!exists_test(attr)) die("attribute file " + attr + " not find ");
@@ -88,17 +87,9 @@ static GraphHost load_graph(const string& folder, bool need_edges, bool need_in)
         int64_t kept = fora_host_read_edges(gf.c_str(), g.n, nullptr, nullptr);
         if (kept == FORA_ERANGE) die("graph.txt: node id >= n (the reference asserts t1 < n, graph.h:155)");
         if (kept < 0) die("cannot read " + gf);
-        vector<int32_t> src((size_t)kept), dst((size_t)kept);
-        fora_host_read_edges(gf.c_str(), g.n, src.data(), dst.data());
-        g.out_ptr.resize((size_t)g.n + 1);
-        g.out_col.resize((size_t)max<int64_t>(kept, 1));
-        if (need_in) {
-            g.in_ptr.resize((size_t)g.n + 1);
-            g.in_col.resize((size_t)max<int64_t>(kept, 1));
-        }
-        if (fora_host_csr_from_edges(g.n, kept, src.data(), dst.data(), g.out_ptr.data(), g.out_col.data(),
-                                     need_in ? g.in_ptr.data() : nullptr, need_in ? g.in_col.data() : nullptr))
-            die("csr construction failed");
+        g.src.resize((size_t)kept);
+        g.dst.resize((size_t)kept);
+        fora_host_read_edges(gf.c_str(), g.n, g.src.data(), g.dst.data());
     }
     cout << "init graph n: " << g.n << " m: " << g.m << endl;
     return g;
@@ -152,8 +143,7 @@ static vector<Gpu> open_gpus(const GraphHost& g, bool need_in) {
     for (int d = 0; d < config.gpus; ++d) {
         if (fora_ctx_create(d, seed, &gp[d].ctx)) die(string("fora_b200: ") + fora_last_error(nullptr));
         CKF(gp[d].ctx, fora_ctx_set_slots(gp[d].ctx, config.slots));
-        CKF(gp[d].ctx, fora_graph_upload(gp[d].ctx, g.n, g.m, g.out_ptr.data(), g.out_col.data(), need_in ? g.in_ptr.data() : nullptr,
-                                         need_in ? g.in_col.data() : nullptr));
+        CKF(gp[d].ctx, fora_graph_build_from_edges(gp[d].ctx, g.n, g.m, g.src.data(), g.dst.data(), (int64_t)g.src.size(), need_in ? 1 : 0));
     }
     return gp;
 }
@@ -602,11 +592,11 @@ int main(int argc, char* argv[]) {
     config.graph_location = config.get_graph_folder();
     Result result;
     if (config.action == "generate-ss-query") {
-        GraphHost g = load_graph(config.graph_location, false, false);
+        GraphHost g = load_graph(config.graph_location, false);
         generate_ss_query(g.n);
     } else if (config.action == "query" || config.action == "topk" || config.action == "batch-topk" || config.action == "gen-exact-topk" || config.action == "build") {
         const bool need_in = config.algo == "bippr";
-        GraphHost g = load_graph(config.graph_location, true, need_in);
+        GraphHost g = load_graph(config.graph_location, true);
         cout << "load graph finish" << endl;
         config.delta = 1.0 / g.n; // init_parameter, graph.h:173-183
         config.pfail = 1.0 / g.n;
