@@ -102,6 +102,7 @@ def lib():
     L.fora_device_reserve.argtypes = [vp, C.c_int]
     L.fora_device_residue.restype = vp
     L.fora_device_residue.argtypes = [vp, C.c_int]
+    L.fora_device_to_original.argtypes = [vp, vp, vp]
     L.fora_compute_ppr_part_device.argtypes = [vp, C.c_double, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(QueryStat)]
     L.fora_topk_batch.argtypes = [vp, C.c_int, c_ip, C.c_int32, C.c_uint32, c_ip, c_dp, c_ip, C.POINTER(QueryStat), C.POINTER(BatchTiming)]
     L.fora_topk_of.argtypes = [vp, c_dp, C.c_uint32, c_ip, c_dp]
@@ -312,6 +313,9 @@ class Engine:
 
     def device_residue_ptr(self, slot=0):
         return self.L.fora_device_residue(self.h, slot)
+
+    def device_to_original(self, d_internal_ptr, d_original_ptr):
+        self._ck(self.L.fora_device_to_original(self.h, C.c_void_p(d_internal_ptr), C.c_void_p(d_original_ptr)))
 
     def compute_ppr_part_device(self, rsum, qid, part, nparts):
         st = QueryStat()

@@ -38,6 +38,10 @@ struct DeviceGraph {
     int64_t* in_ptr64 = nullptr;
     u32* in_ptr32 = nullptr;
     int32_t* in_col = nullptr;
+    // internal relabelling by descending in-degree (engine.cu): kernels see new ids, the ABI speaks original ids
+    bool relabeled = false;
+    int32_t* old2new = nullptr;
+    int32_t* new2old = nullptr;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -78,6 +78,7 @@ struct fora_ctx {
     std::string err;
     int num_sms = 0;
     DeviceGraph g;
+    std::vector<int32_t> h_old2new, h_new2old; // host copies of the internal relabelling (empty: identity)
     fora_params p{};
     bool params_set = false;
     int slots = 16;
@@ -168,6 +169,11 @@ struct fora_ctx {
 // --balanced cost model, calibrated on B200 with the LiveJournal-shape graph (profiles/):
 // walks ~8.5 G/s (no-zero-hop, ~4.9 hops each); push ~28 G edges/s in the scatter phase and ~10 G
 // vertices/s in the gather phase with residue+deg pinned in L2; ~10 us of barrier latency per level.
+static int relabel_graph(fora_ctx* ctx);
+
+static int permute_csr(fora_ctx* ctx, int32_t n, int64_t ne, const int32_t* src_of, const int32_t* map, const int64_t* in_ptr,
+                       const int32_t* in_col, int64_t** out_ptr, int32_t** out_col);
+
 static const double DEFAULT_COST_WALK = 1.2e-10;   // s per online walk
 static const double DEFAULT_COST_EDGE = 3.5e-11;   // s per pushed edge
 static const double DEFAULT_COST_VERTEX = 1.0e-10; // s per pushed vertex
@@ -227,6 +233,7 @@ extern "C" int fora_ctx_create(int device, uint64_t seed, fora_ctx** out) {
 static void free_graph(DeviceGraph& g) {
     cudaFree(g.out_ptr64); cudaFree(g.out_ptr32); cudaFree(g.out_col); cudaFree(g.deg);
     cudaFree(g.in_ptr64); cudaFree(g.in_ptr32); cudaFree(g.in_col);
+    cudaFree(g.old2new); cudaFree(g.new2old);
     g = DeviceGraph();
 }
 
@@ -322,7 +329,8 @@ extern "C" int fora_graph_upload(fora_ctx* ctx, int32_t n, int64_t m_decl, const
     ctx->alloc_slots = 0; // dense state is sized by n
     ctx->has_index = false;
     ctx->session_source = -1;
-    return FORA_OK;
+    ctx->bwd_blocks = 0;
+    return relabel_graph(ctx);
 }
 
 extern "C" int fora_graph_download_csr(fora_ctx* ctx, int64_t* out_ptr, int32_t* out_col, int64_t* in_ptr, int32_t* in_col) {
@@ -330,14 +338,25 @@ extern "C" int fora_graph_download_csr(fora_ctx* ctx, int64_t* out_ptr, int32_t*
     CK(cudaSetDevice(ctx->device));
     const DeviceGraph& g = ctx->g;
     const size_t ne = (size_t)g.n_edges;
-    if (out_ptr) CK(cudaMemcpyAsync(out_ptr, g.out_ptr64, sizeof(int64_t) * (size_t)(g.n + 1), cudaMemcpyDeviceToHost, ctx->stream));
-    if (out_col) CK(cudaMemcpyAsync(out_col, g.out_col, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost, ctx->stream));
-    if (in_ptr || in_col) {
-        if (!g.has_in) return ctx->fail(FORA_EINVAL, "in-CSR was not uploaded");
-        if (in_ptr) CK(cudaMemcpyAsync(in_ptr, g.in_ptr64, sizeof(int64_t) * (size_t)(g.n + 1), cudaMemcpyDeviceToHost, ctx->stream));
-        if (in_col) CK(cudaMemcpyAsync(in_col, g.in_col, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((in_ptr || in_col) && !g.has_in) return ctx->fail(FORA_EINVAL, "in-CSR was not uploaded");
+    // the kernels work on a relabelled copy; the download undoes the permutation (bit-exact original lists)
+    int64_t *optr = g.out_ptr64, *iptr = g.in_ptr64, *t_optr = nullptr, *t_iptr = nullptr;
+    int32_t *ocol = g.out_col, *icol = g.in_col, *t_ocol = nullptr, *t_icol = nullptr;
+    int rc;
+    if (g.relabeled) {
+        if ((rc = permute_csr(ctx, g.n, g.n_edges, g.old2new, g.new2old, g.out_ptr64, g.out_col, &t_optr, &t_ocol))) return rc;
+        optr = t_optr; ocol = t_ocol;
+        if (in_ptr || in_col) {
+            if ((rc = permute_csr(ctx, g.n, g.n_edges, g.old2new, g.new2old, g.in_ptr64, g.in_col, &t_iptr, &t_icol))) return rc;
+            iptr = t_iptr; icol = t_icol;
+        }
     }
+    if (out_ptr) CK(cudaMemcpyAsync(out_ptr, optr, sizeof(int64_t) * (size_t)(g.n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_col) CK(cudaMemcpyAsync(out_col, ocol, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost, ctx->stream));
+    if (in_ptr) CK(cudaMemcpyAsync(in_ptr, iptr, sizeof(int64_t) * (size_t)(g.n + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    if (in_col) CK(cudaMemcpyAsync(in_col, icol, sizeof(int32_t) * ne, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    cudaFree(t_optr); cudaFree(t_ocol); cudaFree(t_iptr); cudaFree(t_icol);
     return FORA_OK;
 }
 extern "C" int64_t fora_graph_num_edges(fora_ctx* ctx) { return ctx ? ctx->g.n_edges : FORA_EINVAL; }
@@ -455,6 +474,151 @@ extern "C" int fora_graph_build_from_edges(fora_ctx* ctx, int32_t n, int64_t m_d
     ctx->has_index = false;
     ctx->session_source = -1;
     ctx->bwd_blocks = 0;
+    return relabel_graph(ctx);
+}
+
+
+// =============================================================================================
+// Internal relabelling by descending in-degree.  Where a walk or a push lands is distributed like the
+// in-degree, so after the renumbering the hot entries of every per-vertex vector (residue, ppr, row offsets) and
+// the adjacency lists of the hot vertices are contiguous and stay in the L2 (measured on the LJ-shape graph:
+// +11 % queries/s).  Every adjacency list keeps its internal order.  The ABI keeps speaking ORIGINAL ids: sources,
+// dense vectors, top-k ids, index files and the CSR download are mapped at the boundary.
+// =============================================================================================
+__global__ void indeg_kernel(int64_t ne, const int32_t* __restrict__ col, u32* __restrict__ indeg) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) atomicAdd(&indeg[col[e]], 1u);
+}
+__global__ void relabel_key_kernel(int32_t n, const u32* __restrict__ indeg, u32* __restrict__ keys, int32_t* __restrict__ ids) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        keys[v] = 0xffffffffu - indeg[v]; // ascending key == descending in-degree; the stable sort keeps id order among ties
+        ids[v] = v;
+    }
+}
+__global__ void invert_perm_kernel(int32_t n, const int32_t* __restrict__ fwd, int32_t* __restrict__ inv) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) inv[fwd[v]] = v;
+}
+// output vertex i takes the adjacency list of input vertex src_of[i]; every neighbour id goes through map[]
+__global__ void permute_deg_kernel(int32_t n, const int32_t* __restrict__ src_of, const int64_t* __restrict__ in_ptr,
+                                   unsigned long long* __restrict__ cnt) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x)
+        cnt[i] = i < n ? (unsigned long long)(in_ptr[src_of[i] + 1] - in_ptr[src_of[i]]) : 0ull;
+}
+__global__ void permute_fill_kernel(int32_t n, const int32_t* __restrict__ src_of, const int32_t* __restrict__ map,
+                                    const int64_t* __restrict__ in_ptr, const int32_t* __restrict__ in_col,
+                                    const int64_t* __restrict__ out_ptr, int32_t* __restrict__ out_col) {
+    const int lane = threadIdx.x & 31;
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += (gridDim.x * blockDim.x) >> 5) {
+        const int64_t ib = in_ptr[src_of[i]], d = in_ptr[src_of[i] + 1] - ib, ob = out_ptr[i];
+        for (int64_t k = lane; k < d; k += 32) out_col[ob + k] = map[in_col[ib + k]];
+    }
+}
+template <typename T>
+__global__ void gather_kernel(size_t n, const T* __restrict__ src, const int32_t* __restrict__ idx, T* __restrict__ dst) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[idx[i]];
+}
+__global__ void map_ids_kernel(size_t n, const int32_t* __restrict__ in, const int32_t* __restrict__ map, int32_t* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i] < 0 ? in[i] : map[in[i]];
+}
+
+// CSR (in_ptr, in_col) -> freshly allocated (out_ptr, out_col) under the permutation (src_of, map)
+static int permute_csr(fora_ctx* ctx, int32_t n, int64_t ne, const int32_t* src_of, const int32_t* map, const int64_t* in_ptr,
+                       const int32_t* in_col, int64_t** out_ptr, int32_t** out_col) {
+    DevBuf<unsigned long long> cnt;
+    DevBuf<unsigned char> tmp;
+    CK(cnt.ensure((size_t)n + 1));
+    CK(cudaMalloc((void**)out_ptr, sizeof(int64_t) * ((size_t)n + 1)));
+    CK(cudaMalloc((void**)out_col, sizeof(int32_t) * std::max<size_t>((size_t)ne, 1)));
+    permute_deg_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, src_of, in_ptr, cnt.p);
+    CKL();
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, bytes, cnt.p, (unsigned long long*)*out_ptr, n + 1, ctx->stream));
+    CK(tmp.ensure(bytes));
+    CK(cub::DeviceScan::ExclusiveSum(tmp.p, bytes, cnt.p, (unsigned long long*)*out_ptr, n + 1, ctx->stream));
+    permute_fill_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, src_of, map, in_ptr, in_col, *out_ptr, *out_col);
+    CKL();
+    CK(cudaStreamSynchronize(ctx->stream));
+    cnt.release(); tmp.release();
+    return FORA_OK;
+}
+
+static int relabel_graph(fora_ctx* ctx) {
+    DeviceGraph& g = ctx->g;
+    ctx->h_old2new.clear();
+    ctx->h_new2old.clear();
+    if (getenv("FORA_NO_RELABEL") || g.n < 2) return FORA_OK;
+    const int32_t n = g.n;
+    DevBuf<u32> indeg, keys, keys_out;
+    DevBuf<int32_t> ids;
+    DevBuf<unsigned char> tmp;
+    CK(indeg.ensure((size_t)n)); CK(keys.ensure((size_t)n)); CK(keys_out.ensure((size_t)n)); CK(ids.ensure((size_t)n));
+    CK(cudaMalloc((void**)&g.old2new, sizeof(int32_t) * (size_t)n));
+    CK(cudaMalloc((void**)&g.new2old, sizeof(int32_t) * (size_t)n));
+    CK(cudaMemsetAsync(indeg.p, 0, sizeof(u32) * (size_t)n, ctx->stream));
+    if (g.n_edges > 0) {
+        indeg_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(g.n_edges, g.out_col, indeg.p);
+        CKL();
+    }
+    relabel_key_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, indeg.p, keys.p, ids.p);
+    CKL();
+    size_t bytes = 0;
+    CK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, keys.p, keys_out.p, ids.p, g.new2old, n, 0, 32, ctx->stream));
+    CK(tmp.ensure(bytes));
+    CK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, keys.p, keys_out.p, ids.p, g.new2old, n, 0, 32, ctx->stream));
+    invert_perm_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.new2old, g.old2new);
+    CKL();
+    int64_t* nptr = nullptr;
+    int32_t* ncol = nullptr;
+    int rc = permute_csr(ctx, n, g.n_edges, g.new2old, g.old2new, g.out_ptr64, g.out_col, &nptr, &ncol);
+    if (rc) return rc;
+    cudaFree(g.out_ptr64); cudaFree(g.out_col);
+    g.out_ptr64 = nptr; g.out_col = ncol;
+    degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.out_ptr64, g.deg, g.out_ptr32);
+    CKL();
+    if (g.has_in) {
+        if ((rc = permute_csr(ctx, n, g.n_edges, g.new2old, g.old2new, g.in_ptr64, g.in_col, &nptr, &ncol))) return rc;
+        cudaFree(g.in_ptr64); cudaFree(g.in_col);
+        g.in_ptr64 = nptr; g.in_col = ncol;
+        if (g.off32) {
+            DevBuf<int32_t> t2;
+            CK(t2.ensure((size_t)n));
+            degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.in_ptr64, t2.p, g.in_ptr32);
+            CKL();
+            CK(cudaStreamSynchronize(ctx->stream));
+            t2.release();
+        }
+    }
+    ctx->h_old2new.resize((size_t)n);
+    ctx->h_new2old.resize((size_t)n);
+    CK(cudaMemcpyAsync(ctx->h_old2new.data(), g.old2new, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->h_new2old.data(), g.new2old, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    g.relabeled = true;
+    indeg.release(); keys.release(); keys_out.release(); ids.release(); tmp.release();
+    return FORA_OK;
+}
+
+static inline int32_t to_internal(const fora_ctx* ctx, int32_t v) { return ctx->g.relabeled ? ctx->h_old2new[(size_t)v] : v; }
+static inline int32_t to_original(const fora_ctx* ctx, int32_t v) { return ctx->g.relabeled ? ctx->h_new2old[(size_t)v] : v; }
+
+// dense per-vertex vector, internal order (device) -> original order (device); dst != src
+template <typename T>
+static int vec_to_original(fora_ctx* ctx, const T* d_src, T* d_dst, size_t n) {
+    if (!ctx->g.relabeled) {
+        CK(cudaMemcpyAsync(d_dst, d_src, sizeof(T) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        return FORA_OK;
+    }
+    gather_kernel<T><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, d_src, ctx->g.old2new, d_dst); // dst[old] = src[old2new[old]]
+    CKL();
+    return FORA_OK;
+}
+template <typename T>
+static int vec_to_internal(fora_ctx* ctx, const T* d_src, T* d_dst, size_t n) {
+    if (!ctx->g.relabeled) {
+        CK(cudaMemcpyAsync(d_dst, d_src, sizeof(T) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+        return FORA_OK;
+    }
+    gather_kernel<T><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, d_src, ctx->g.new2old, d_dst); // dst[new] = src[new2old[new]]
+    CKL();
     return FORA_OK;
 }
 
@@ -699,7 +863,12 @@ static int init_wave(fora_ctx* ctx, int cnt, int seed_source, const int32_t* d_s
     ctx->level_base = 0;
     int rc = meta_h2d(ctx);
     if (rc) return rc;
-    if (d_sources) CK(cudaMemcpyAsync(ctx->meta.p->source, d_sources, sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (d_sources) {
+        if (ctx->g.relabeled) {
+            map_ids_kernel<<<1, 64, 0, ctx->stream>>>((size_t)cnt, d_sources, ctx->g.old2new, ctx->meta.p->source);
+            CKL();
+        } else CK(cudaMemcpyAsync(ctx->meta.p->source, d_sources, sizeof(int32_t) * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     CK(cudaMemsetAsync(ctx->reserve.p, 0, sizeof(double) * n * cnt, ctx->stream));
     CK(cudaMemsetAsync(ctx->residue.p, 0, sizeof(double) * n * cnt, ctx->stream));
     CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
@@ -825,7 +994,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.part = part; wa.nparts = nparts;
     wa.round_tag = round_tag; wa.ppr = ppr; wa.hops = m->hops; wa.idx_hits = m->idx_hits;
     wa.idx_off = ctx->idx_off.p; wa.idx_cnt = ctx->idx_cnt.p; wa.idx_dest = ctx->idx_dest.p; wa.idx_used = idx_used;
-    const int wgx = ctx->num_sms * 8;
+    const int wgx = ctx->num_sms * (getenv("FORA_WALK_GRID") ? atoi(getenv("FORA_WALK_GRID")) : 8);
     if (ppr == ctx->reserve.p) {
         int wrc = set_l2_window(ctx, ctx->win_walk_off, ctx->win_walk_bytes);
         if (wrc) return wrc;
@@ -873,8 +1042,16 @@ static int require_ready(fora_ctx* ctx, double omega_max) {
 
 static int download_fwd(fora_ctx* ctx, int slot, double* reserve, double* residue) {
     const size_t n = (size_t)ctx->g.n;
-    if (reserve) CK(cudaMemcpyAsync(reserve, ctx->reserve.p + n * slot, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (residue) CK(cudaMemcpyAsync(residue, ctx->residue.p + n * slot, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc;
+    CK(ctx->scratchd.ensure(n));
+    if (reserve) {
+        if ((rc = vec_to_original(ctx, ctx->reserve.p + n * slot, ctx->scratchd.p, n))) return rc;
+        CK(cudaMemcpyAsync(reserve, ctx->scratchd.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (residue) {
+        if ((rc = vec_to_original(ctx, ctx->residue.p + n * slot, ctx->scratchd.p, n))) return rc;
+        CK(cudaMemcpyAsync(residue, ctx->scratchd.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     return FORA_OK;
 }
@@ -888,7 +1065,7 @@ extern "C" int fora_push_only(fora_ctx* ctx, int32_t source, double rmax, double
     const int keep_bal = ctx->p.balanced;
     ctx->p.rmax = rmax;
     ctx->p.balanced = 0;
-    ctx->h_meta->source[0] = source;
+    ctx->h_meta->source[0] = to_internal(ctx, source);
     ctx->h_meta->qid[0] = 0;
     double fr;
     u64 rounds;
@@ -907,7 +1084,7 @@ extern "C" int fora_push_begin(fora_ctx* ctx, int32_t source) {
     int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
     if (rc) return rc;
     if (source < 0 || source >= ctx->g.n) return ctx->fail(FORA_EINVAL, "source out of range");
-    ctx->h_meta->source[0] = source;
+    ctx->h_meta->source[0] = to_internal(ctx, source);
     ctx->h_meta->qid[0] = 0;
     if ((rc = init_wave(ctx, 1, 0, nullptr))) return rc;
     if ((rc = meta_d2h_sync(ctx))) return rc;
@@ -964,6 +1141,7 @@ extern "C" int fora_random_walks(fora_ctx* ctx, int32_t start, int64_t count, in
     ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
     ba.key_tag = 0x77a1c5u;
     ba.single = start; ba.total = (u64)count; ba.dest = ctx->scratch32.p; ba.counts = nullptr; ba.hops = ctx->scratch64.p;
+    ba.old2new = ctx->g.relabeled ? ctx->g.old2new : nullptr; ba.new2old = ctx->g.relabeled ? ctx->g.new2old : nullptr;
     int rc = launch_bulk(ctx, ba, no_zero_hop);
     if (rc) return rc;
     if (dest) CK(cudaMemcpyAsync(dest, ctx->scratch32.p, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
@@ -985,12 +1163,16 @@ extern "C" int fora_compute_ppr(fora_ctx* ctx, const double* reserve, const doub
     h->state[0] = rsum == 0.0 ? 2 : 1; // query.h:267-268: rsum == 0 -> ppr = reserve only
     h->rsum[0] = rsum;
     if ((rc = meta_h2d(ctx))) return rc;
-    CK(cudaMemcpyAsync(ctx->reserve.p, reserve, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->residue.p, residue, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx->scratchd.ensure(n));
+    CK(cudaMemcpyAsync(ctx->scratchd.p, reserve, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vec_to_internal(ctx, ctx->scratchd.p, ctx->reserve.p, n))) return rc;
+    CK(cudaMemcpyAsync(ctx->scratchd.p, residue, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = vec_to_internal(ctx, ctx->scratchd.p, ctx->residue.p, n))) return rc;
     if ((rc = walk_wave(ctx, ctx->reserve.p, 0, ctx->p.opt, ctx->p.opt, 0, nullptr))) return rc;
     if ((rc = meta_d2h_sync(ctx))) return rc;
     if (stat) fill_stat(ctx, 0, ctx->p.rmax, 0, stat);
-    CK(cudaMemcpyAsync(ppr, ctx->reserve.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = vec_to_original(ctx, ctx->reserve.p, ctx->scratchd.p, n))) return rc;
+    CK(cudaMemcpyAsync(ppr, ctx->scratchd.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->session_source = -1;
     return FORA_OK;
@@ -1044,9 +1226,17 @@ extern "C" int fora_reverse_push(fora_ctx* ctx, int32_t target, double rmax, dou
     CK(ctx->scratch32.ensure(4));
     CK(cudaMemsetAsync(ctx->scratchd.p, 0, sizeof(double) * n, ctx->stream));
     CK(cudaMemsetAsync(ctx->scratch32.p, 0, sizeof(int32_t) * 4, ctx->stream));
-    if ((rc = launch_bwd(ctx, -1, rmax, 1.0, nullptr, nullptr, target, target + 1, ctx->scratchd.p, 1, nullptr, ctx->scratch32.p))) return rc;
-    if (reserve) CK(cudaMemcpyAsync(reserve, ctx->scratchd.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    if (residue) CK(cudaMemcpyAsync(residue, ctx->bwd_res.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    const int32_t t_int = to_internal(ctx, target);
+    if ((rc = launch_bwd(ctx, -1, rmax, 1.0, nullptr, nullptr, t_int, t_int + 1, ctx->scratchd.p, 1, nullptr, ctx->scratch32.p))) return rc;
+    CK(ctx->stage.ensure(n));
+    if (reserve) {
+        if ((rc = vec_to_original(ctx, ctx->scratchd.p, ctx->stage.p, n))) return rc;
+        CK(cudaMemcpyAsync(reserve, ctx->stage.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (residue) {
+        if ((rc = vec_to_original(ctx, ctx->bwd_res.p, ctx->stage.p, n))) return rc;
+        CK(cudaMemcpyAsync(residue, ctx->stage.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    }
     // the hook left block 0's scratch dirty: wipe it (dense memset, test path only)
     CK(cudaMemsetAsync(ctx->bwd_res.p, 0, sizeof(double) * n, ctx->stream));
     int32_t ovf = 0;
@@ -1107,6 +1297,15 @@ extern "C" void* fora_device_residue(fora_ctx* ctx, int slot) {
     return ctx->residue.p + (size_t)ctx->g.n * slot;
 }
 extern "C" int fora_prepare_slots(fora_ctx* ctx) { return require_ready(ctx, ctx ? ctx->p.omega : 0); }
+// dense vector in the engine's internal vertex order (what the device pointers above hold) -> original ids
+extern "C" int fora_device_to_original(fora_ctx* ctx, const double* d_internal, double* d_original) {
+    if (!ctx || !ctx->g.n || !d_internal || !d_original || d_internal == d_original) return ctx ? ctx->fail(FORA_EINVAL, "bad arguments") : FORA_EINVAL;
+    CK(cudaSetDevice(ctx->device));
+    int rc = vec_to_original(ctx, d_internal, d_original, (size_t)ctx->g.n);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
 
 extern "C" int fora_compute_ppr_part_device(fora_ctx* ctx, double rsum, uint32_t qid, uint32_t part, uint32_t nparts, fora_query_stat* stat) {
     int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
@@ -1156,7 +1355,7 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
         for (int s = 0; s < cnt; ++s) {
             if (h_sources) {
                 if (h_sources[q0 + s] < 0 || h_sources[q0 + s] >= ctx->g.n) return ctx->fail(FORA_EINVAL, "source out of range");
-                h->source[s] = h_sources[q0 + s];
+                h->source[s] = to_internal(ctx, h_sources[q0 + s]);
             } else h->source[s] = 0;
             h->qid[s] = (u32)(q0 + s);
         }
@@ -1200,7 +1399,7 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
                     int32_t sv;
                     CK(cudaMemcpyAsync(&sv, d_sources + q0 + s, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
                     CK(cudaStreamSynchronize(ctx->stream));
-                    ba.single = sv;
+                    ba.single = to_internal(ctx, sv);
                 }
                 if ((rc = launch_bulk(ctx, ba, 0))) return rc;
                 counts_to_ppr_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->g.n, ctx->counts.p, ctx->p.omega, ctx->reserve.p + n * s);
@@ -1215,7 +1414,8 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
             // overlaps the computation of wave w+1 (the slot vectors are re-initialised immediately)
             CK(ctx->stage.ensure(n * (size_t)S));
             if (ctx->stage_busy) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
-            CK(cudaMemcpyAsync(ctx->stage.p, ctx->reserve.p, sizeof(double) * n * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
+            for (int s = 0; s < cnt; ++s)
+                if ((rc = vec_to_original(ctx, ctx->reserve.p + n * s, ctx->stage.p + n * s, n))) return rc; // back to original ids
             CK(cudaEventRecord(ctx->ev_stage_ready, ctx->stream));
             CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_ready, 0));
             CK(cudaMemcpyAsync(ppr + (size_t)q0 * n, ctx->stage.p, sizeof(double) * n * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -1316,7 +1516,7 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
         const int cnt = std::min<int32_t>(S, n_q - q0);
         for (int s = 0; s < cnt; ++s) {
             if (sources[q0 + s] < 0 || sources[q0 + s] >= n) return restore(ctx->fail(FORA_EINVAL, "source out of range"));
-            h->source[s] = sources[q0 + s];
+            h->source[s] = to_internal(ctx, sources[q0 + s]);
             h->qid[s] = (u32)(q0 + s);
         }
         const double* result = ctx->reserve.p; // where each slot's final vector lives
@@ -1500,6 +1700,12 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
         for (int s = 0; s < cnt; ++s) { // topk_ppr(), algo.h:592-610
             cudaError_t e = topk_device(ctx->stream, ctx->num_sms, result + nn * s, n, k, nodes + (size_t)(q0 + s) * k, values + (size_t)(q0 + s) * k, &ctx->launches);
             if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("topk: ") + cudaGetErrorString(e)));
+            if (ctx->g.relabeled) { // internal -> original ids; unfilled slots stay (0, 0.0)
+                int32_t* nd = nodes + (size_t)(q0 + s) * k;
+                const double* vl = values + (size_t)(q0 + s) * k;
+                for (uint32_t j = 0; j < k; ++j)
+                    if (vl[j] > 0.0) nd[j] = to_original(ctx, nd[j]);
+            }
         }
         CK(cudaEventRecord(ctx->ev[7], ctx->stream));
         CK(cudaEventSynchronize(ctx->ev[7]));
@@ -1540,8 +1746,9 @@ extern "C" int fora_index_info(fora_ctx* ctx, uint64_t* offsets, uint64_t* count
     if (!ctx->params_set || !offsets || !counts) return ctx->fail(FORA_EINVAL, "params / outputs missing");
     CK(cudaSetDevice(ctx->device));
     const int32_t n = ctx->g.n;
-    std::vector<int32_t> deg((size_t)n);
-    CK(cudaMemcpy(deg.data(), ctx->g.deg, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> deg_int((size_t)n), deg((size_t)n);
+    CK(cudaMemcpy(deg_int.data(), ctx->g.deg, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost));
+    for (int32_t v = 0; v < n; ++v) deg[(size_t)v] = deg_int[(size_t)to_internal(ctx, v)]; // offsets / counts are per ORIGINAL vertex id
     // build.h:325-334 -- host arithmetic in the reference's expression order (bit-exact counts)
     const fora_params& p = ctx->p;
     u64 tuned = 0;
@@ -1581,6 +1788,7 @@ extern "C" int fora_index_build(fora_ctx* ctx, const uint64_t* offsets, const ui
     ba.key_tag = 0x1d800000u;
     ba.seg_off = ctx->scratch64.p + 1; ba.v_begin = v_begin; ba.single = -1; ba.nseg = nseg; ba.total = total;
     ba.dest = ctx->scratch32.p; ba.counts = nullptr; ba.hops = ctx->scratch64.p;
+    ba.old2new = ctx->g.relabeled ? ctx->g.old2new : nullptr; ba.new2old = ctx->g.relabeled ? ctx->g.new2old : nullptr;
     int rc = launch_bulk(ctx, ba, ctx->p.opt); // build.h:347-350
     if (rc) return rc;
     CK(cudaMemcpyAsync(dest, ctx->scratch32.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1597,10 +1805,30 @@ extern "C" int fora_index_upload(fora_ctx* ctx, const uint64_t* offsets, const u
     CK(ctx->idx_off.ensure(n));
     CK(ctx->idx_cnt.ensure(n));
     CK(ctx->idx_dest.ensure(std::max<size_t>(len, 1)));
-    CK(cudaMemcpyAsync(ctx->idx_off.p, offsets, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->idx_cnt.p, counts, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->idx_dest.p, dest, sizeof(int32_t) * len, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->g.relabeled) { // per-vertex info permuted to internal order, destinations mapped to internal ids
+        DevBuf<u64> t64;
+        DevBuf<int32_t> t32;
+        CK(t64.ensure(n));
+        CK(t32.ensure(std::max<size_t>(len, 1)));
+        CK(cudaMemcpyAsync(t64.p, offsets, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+        gather_kernel<u64><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, t64.p, ctx->g.new2old, ctx->idx_off.p);
+        CKL();
+        CK(cudaMemcpyAsync(t64.p, counts, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+        gather_kernel<u64><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, t64.p, ctx->g.new2old, ctx->idx_cnt.p);
+        CKL();
+        CK(cudaMemcpyAsync(t32.p, dest, sizeof(int32_t) * len, cudaMemcpyHostToDevice, ctx->stream));
+        if (len) {
+            map_ids_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(len, t32.p, ctx->g.old2new, ctx->idx_dest.p);
+            CKL();
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        t64.release(); t32.release();
+    } else {
+        CK(cudaMemcpyAsync(ctx->idx_off.p, offsets, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->idx_cnt.p, counts, sizeof(u64) * n, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->idx_dest.p, dest, sizeof(int32_t) * len, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->has_index = true;
     return FORA_OK;
 }
@@ -1629,10 +1857,13 @@ extern "C" int fora_power_iteration(fora_ctx* ctx, int32_t source, int iters, do
     const size_t n = (size_t)ctx->g.n;
     CK(ctx->scratchd.ensure(3 * n + 2));
     cudaError_t e;
-    if (ctx->g.off32) e = power_iteration_device<u32>(ctx->stream, ctx->num_sms, CsrView<u32>{ctx->g.out_ptr32, ctx->g.out_col}, ctx->g.n, source, iters, ctx->p.alpha, ctx->scratchd.p, &ctx->launches);
-    else e = power_iteration_device<int64_t>(ctx->stream, ctx->num_sms, CsrView<int64_t>{ctx->g.out_ptr64, ctx->g.out_col}, ctx->g.n, source, iters, ctx->p.alpha, ctx->scratchd.p, &ctx->launches);
+    if (ctx->g.off32) e = power_iteration_device<u32>(ctx->stream, ctx->num_sms, CsrView<u32>{ctx->g.out_ptr32, ctx->g.out_col}, ctx->g.n, to_internal(ctx, source), iters, ctx->p.alpha, ctx->scratchd.p, &ctx->launches);
+    else e = power_iteration_device<int64_t>(ctx->stream, ctx->num_sms, CsrView<int64_t>{ctx->g.out_ptr64, ctx->g.out_col}, ctx->g.n, to_internal(ctx, source), iters, ctx->p.alpha, ctx->scratchd.p, &ctx->launches);
     if (e != cudaSuccess) return ctx->fail(FORA_ECUDA, std::string("power iteration: ") + cudaGetErrorString(e));
-    CK(cudaMemcpyAsync(ppr, ctx->scratchd.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx->stage.ensure(n));
+    int prc = vec_to_original(ctx, ctx->scratchd.p, ctx->stage.p, n);
+    if (prc) return prc;
+    CK(cudaMemcpyAsync(ppr, ctx->stage.p, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return FORA_OK;
 }

@@ -30,10 +30,22 @@ constexpr int MAX_SLOTS = 64; // also bounded by the 8 slot bits of a frontier e
 constexpr int MAX_PUSH_CTAS = 512;
 constexpr u32 TILE_MIN = 2048;   // smallest edge range worth giving to a CTA
 constexpr u32 TILE_MAX = 16384;  // tiles of a large level: the grid sweeps the edge line 296*16K edges at a time
-constexpr int PUSH_UA = 4;       // frontier entries per thread per phase-A batch
-constexpr int PUSH_BATCH = 1024; // frontier entries staged in shared memory per phase-B batch
-constexpr int PUSH_UB = 4;       // edges in flight per lane in phase B
-constexpr int PUSH_WQ = 256;     // per-warp queue of crossing vertices
+#ifndef CFG_PUSH_UA
+#define CFG_PUSH_UA 4
+#endif
+constexpr int PUSH_UA = CFG_PUSH_UA;       // frontier entries per thread per phase-A batch
+#ifndef CFG_PUSH_BATCH
+#define CFG_PUSH_BATCH 1024
+#endif
+constexpr int PUSH_BATCH = CFG_PUSH_BATCH; // frontier entries staged in shared memory per phase-B batch
+#ifndef CFG_PUSH_UB
+#define CFG_PUSH_UB 2
+#endif
+constexpr int PUSH_UB = CFG_PUSH_UB;       // edges in flight per lane in phase B
+#ifndef CFG_PUSH_WQ
+#define CFG_PUSH_WQ 256
+#endif
+constexpr int PUSH_WQ = CFG_PUSH_WQ;     // per-warp queue of crossing vertices
 
 // frontier entry: [slot:8][min(out-degree, 2^24-1):24][vertex:32].  Whoever appends a vertex has just loaded its
 // out-degree for the threshold test, so carrying it saves phase A one random access per vertex.

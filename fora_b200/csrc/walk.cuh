@@ -20,7 +20,10 @@ namespace fora {
 
 constexpr int PLAN_THREADS = 1024;
 constexpr int WALK_THREADS = 256;
-constexpr int WALK_CHUNK = 2048; // walks per chunk (8 per thread)
+#ifndef CFG_WALK_CHUNK
+#define CFG_WALK_CHUNK 1024
+#endif
+constexpr int WALK_CHUNK = CFG_WALK_CHUNK; // walks per chunk (4 per thread; 1024 measured best on B200: less shared memory leaves more L1)
 
 struct PlanArgs {
     int32_t n;
@@ -363,6 +366,8 @@ struct BulkArgs {
     int32_t* __restrict__ dest;        // may be null
     u64* __restrict__ counts;          // [n] destination histogram, may be null
     u64* __restrict__ hops;            // [1]
+    const int32_t* __restrict__ old2new; // internal relabelling (null: identity): starts arrive / destinations leave in original ids
+    const int32_t* __restrict__ new2old;
 };
 
 template <typename OffT, bool NO_ZERO_HOP>
@@ -385,7 +390,8 @@ __global__ void __launch_bounds__(WALK_THREADS) bulk_walk_kernel(BulkArgs a, Csr
             start = a.v_begin + (int32_t)lo;
             j = w - a.seg_off[lo];
         }
-        int32_t cur = start;
+        int32_t cur = a.old2new ? a.old2new[start] : start; // Philox stays keyed by the ORIGINAL start id
+        const int32_t home = cur;
         OffT b = g.ptr[cur];
         u32 d = (u32)(g.ptr[cur + 1] - b);
         if (d != 0) {
@@ -397,18 +403,18 @@ __global__ void __launch_bounds__(WALK_THREADS) bulk_walk_kernel(BulkArgs a, Csr
                 if (!first && rnd.x < a.alpha_thr) break;
                 first = false;
                 if (d) { cur = __ldg(&g.col[b + (OffT)__umulhi(rnd.y, d)]); ++my_hops; }
-                else cur = start;
+                else cur = home;
                 b = g.ptr[cur];
                 d = (u32)(g.ptr[cur + 1] - b);
                 if (rnd.z < a.alpha_thr) break;
                 if (d) { cur = __ldg(&g.col[b + (OffT)__umulhi(rnd.w, d)]); ++my_hops; }
-                else cur = start;
+                else cur = home;
                 b = g.ptr[cur];
                 d = (u32)(g.ptr[cur + 1] - b);
             }
         }
-        if (a.dest) a.dest[w] = cur;
-        if (a.counts) atomicAdd(&a.counts[cur], 1ull);
+        if (a.dest) a.dest[w] = a.new2old ? a.new2old[cur] : cur;
+        if (a.counts) atomicAdd(&a.counts[cur], 1ull); // histogram stays in internal ids
     }
     my_hops = warp_sum(my_hops);
     if (lane_id() == 0 && my_hops) atomicAdd(a.hops, my_hops);

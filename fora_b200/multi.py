@@ -20,8 +20,16 @@ def device_tensor(ptr, n, device):
     return torch.as_tensor(_DevArray(ptr, n), device=device)
 
 
+def to_original(engine, internal_tensor):
+    """dense vector in the engine's internal vertex order -> a new CUDA tensor indexed by original vertex id"""
+    import torch
+    out = torch.empty_like(internal_tensor)
+    engine.device_to_original(internal_tensor.data_ptr(), out.data_ptr())
+    return out
+
+
 def ssppr_split(engine, source, rmax, qid=0, group=None):
-    """returns (ppr as a torch CUDA tensor view of the engine's buffer, stats).  Call on every rank."""
+    """returns (ppr as a torch CUDA tensor indexed by original vertex id, stats).  Call on every rank."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -45,4 +53,4 @@ def ssppr_split(engine, source, rmax, qid=0, group=None):
     if world > 1:
         dist.all_reduce(reserve, op=dist.ReduceOp.SUM, group=group)  # the PPR vector now lives in `reserve` (in place)
     torch.cuda.synchronize()
-    return reserve, stats
+    return to_original(engine, reserve), stats

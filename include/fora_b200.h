@@ -156,7 +156,8 @@ int fora_query_batch(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_
  * on the device (last `slots` queries readable through fora_device_ppr). */
 int fora_query_batch_device(fora_ctx* ctx, int algo, const int32_t* d_sources, int32_t n_q,
                             fora_query_stat* stats, fora_batch_timing* timing);
-/* device pointer (double[n]) of the PPR vector of slot `slot` after the last batch */
+/* device pointer (double[n], internal vertex order -- see fora_device_to_original) of the PPR vector of slot `slot`
+ * after the last batch */
 void* fora_device_ppr(fora_ctx* ctx, int slot);
 
 /* ---- one query split over several GPUs (whole-graph SSPPR at Twitter scale) ----
@@ -166,8 +167,13 @@ void* fora_device_ppr(fora_ctx* ctx, int slot);
  * vector, and the caller reduces the vectors (ncclAllReduce / torch.distributed over NVLink).  part 0 starts from
  * the reserve, the others from zero, so the sum equals the single-GPU result up to fp64 summation order. */
 int fora_prepare_slots(fora_ctx* ctx); /* allocate the per-slot state so the pointers below exist */
-void* fora_device_reserve(fora_ctx* ctx, int slot); /* device double[n] */
-void* fora_device_residue(fora_ctx* ctx, int slot); /* device double[n] */
+/* NOTE: the engine renumbers vertices internally (descending in-degree, for L2 locality).  Everything that crosses the
+ * ABI in HOST buffers is in ORIGINAL ids; the raw device pointers below expose the internal order (identical on every
+ * GPU that holds the same graph, so they can be broadcast / reduced as they are) -- use fora_device_to_original to
+ * obtain a vector indexed by original id. */
+void* fora_device_reserve(fora_ctx* ctx, int slot); /* device double[n], internal order */
+void* fora_device_residue(fora_ctx* ctx, int slot); /* device double[n], internal order */
+int fora_device_to_original(fora_ctx* ctx, const double* d_internal, double* d_original); /* device -> device */
 int fora_compute_ppr_part_device(fora_ctx* ctx, double rsum, uint32_t query_id, uint32_t part, uint32_t nparts,
                                  fora_query_stat* stat); /* result in fora_device_reserve(ctx, 0) */
 

@@ -28,7 +28,7 @@ def test_parts_add_up_to_the_single_gpu_result():
             rmax, omega = E.configure("fora", 0.5, opt=1)
             res, rsd, rsum, _ = E.push_only(s, rmax)   # state stays in slot 0
             E.compute_ppr_part_device(rsum, 0, part, nparts)
-            acc += multi.device_tensor(E.device_reserve_ptr(0), g.n, torch.device("cuda", 0)).cpu().numpy()
+            acc += multi.to_original(E, multi.device_tensor(E.device_reserve_ptr(0), g.n, torch.device("cuda", 0))).cpu().numpy()
             E.close()
         outs[nparts] = acc
     assert np.allclose(outs[1], outs[3], rtol=1e-12, atol=1e-18) and abs(outs[3].sum() - 1.0) < 1e-9
