@@ -166,15 +166,15 @@ struct fora_ctx {
                                              ":" + std::to_string(__LINE__));                   \
     } while (0)
 
-// --balanced cost model, calibrated on B200 with the LiveJournal-shape graph (profiles/):
-// walks ~8.5 G/s (no-zero-hop, ~4.9 hops each); push ~28 G edges/s in the scatter phase and ~10 G
-// vertices/s in the gather phase with residue+deg pinned in L2; ~10 us of barrier latency per level.
 static int relabel_graph(fora_ctx* ctx);
-
 static int permute_csr(fora_ctx* ctx, int32_t n, int64_t ne, const int32_t* src_of, const int32_t* map, const int64_t* in_ptr,
                        const int32_t* in_col, int64_t** out_ptr, int32_t** out_col);
 
-static const double DEFAULT_COST_WALK = 1.2e-10;   // s per online walk
+// --balanced cost model, calibrated on B200 with the LiveJournal-shape graph (profiles/): a walk costs
+// 1.5 ms / 24 M = 6.5e-11 s (no-zero-hop, ~4.9 hops, relabelled graph, 32 slots); push ~3.5e-11 s per edge in the scatter
+// phase plus ~1e-10 s per vertex in the gather phase and ~10 us of barrier latency per level.  With these the loop stops
+// where push time ~ walk time (2.0 ms vs 2.1 ms per query measured), which is what query.h:867-877 aims for.
+static const double DEFAULT_COST_WALK = 6.5e-11;   // s per online walk
 static const double DEFAULT_COST_EDGE = 3.5e-11;   // s per pushed edge
 static const double DEFAULT_COST_VERTEX = 1.0e-10; // s per pushed vertex
 static const double DEFAULT_COST_LEVEL = 1.0e-5;   // s per frontier level
@@ -635,6 +635,11 @@ extern "C" int fora_params_set(fora_ctx* ctx, const fora_params* p) {
         ctx->p.cost_vertex = DEFAULT_COST_VERTEX;
         ctx->p.cost_level = DEFAULT_COST_LEVEL;
     }
+    // development knobs: FORA_COST_WALK / _EDGE / _VERTEX / _LEVEL override the calibration
+    if (getenv("FORA_COST_WALK")) ctx->p.cost_walk = atof(getenv("FORA_COST_WALK"));
+    if (getenv("FORA_COST_EDGE")) ctx->p.cost_edge = atof(getenv("FORA_COST_EDGE"));
+    if (getenv("FORA_COST_VERTEX")) ctx->p.cost_vertex = atof(getenv("FORA_COST_VERTEX"));
+    if (getenv("FORA_COST_LEVEL")) ctx->p.cost_level = atof(getenv("FORA_COST_LEVEL"));
     ctx->params_set = true;
     return FORA_OK;
 }
