@@ -561,7 +561,9 @@ __global__ void __launch_bounds__(256) push_seed_kernel(int32_t n, const int32_t
 constexpr int RED_THREADS = 256;
 // The same dense pass also prepares the NEXT resumable round speculatively: every vertex with
 // residue >= next_rmax*d_out (dangling: any positive residue) is appended to the slot's seed segment, so a
-// round that does continue starts without a second scan of the residue vectors.
+// round that does continue starts without a second scan of the residue vectors.  A block counts its seeds first and
+// reserves their places with ONE global atomic (a per-warp atomic on the per-slot counter serialises at the L2 and
+// made this pass 7x slower than the plain reduction), then writes them in a second sweep over its (L2-hot) range.
 __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n, const double* __restrict__ residue,
                                                                       double* __restrict__ part_sum,
                                                                       u32* __restrict__ part_nnz,
@@ -570,30 +572,27 @@ __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n,
                                                                       u64* __restrict__ seeds, u32* __restrict__ seed_count) {
     __shared__ double s_sum[RED_THREADS];
     __shared__ u32 s_nnz[RED_THREADS];
+    __shared__ u32 s_seed[RED_THREADS];
+    __shared__ u32 s_base;
     const int slot = blockIdx.y;
     const double* __restrict__ res = residue + (size_t)slot * n;
-    const int per_block = (((n + gridDim.x - 1) / gridDim.x) + WARP - 1) / WARP * WARP;
-    const int lo = blockIdx.x * per_block, hi = min(n, lo + per_block);
+    const int per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = min(n, blockIdx.x * per_block), hi = min(n, lo + per_block);
     const double rm = next_rmax ? next_rmax[slot] : 0.0;
     double s = 0.0;
-    u32 c = 0;
-    for (int v0 = lo; v0 < hi; v0 += RED_THREADS) { // warp-uniform trip count (per_block is a multiple of 32)
-        const int v = v0 + threadIdx.x;
-        bool seed = false;
-        int32_t d = 0;
-        if (v < hi) {
-            const double r = res[v];
-            s += r;
-            c += r > 0.0;
-            if (rm > 0.0 && r > 0.0) {
-                d = deg[v];
-                seed = d ? (r >= rm * (double)d) : true;
-            }
+    u32 c = 0, ns = 0;
+    for (int v = lo + threadIdx.x; v < hi; v += RED_THREADS) {
+        const double r = res[v];
+        s += r;
+        c += r > 0.0;
+        if (rm > 0.0 && r > 0.0) {
+            const int32_t d = deg[v];
+            ns += d ? (r >= rm * (double)d) : 1u;
         }
-        if (rm > 0.0 && v0 + (int)(threadIdx.x & ~31u) < hi) warp_append<u64>(seed, make_entry(slot, (u32)d, v), seeds + (size_t)slot * n, &seed_count[slot]);
     }
     s_sum[threadIdx.x] = s;
     s_nnz[threadIdx.x] = c;
+    s_seed[threadIdx.x] = ns;
     __syncthreads();
     for (int o = RED_THREADS / 2; o > 0; o >>= 1) {
         if (threadIdx.x < o) {
@@ -605,6 +604,22 @@ __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n,
     if (threadIdx.x == 0) {
         part_sum[(size_t)slot * gridDim.x + blockIdx.x] = s_sum[0];
         part_nnz[(size_t)slot * gridDim.x + blockIdx.x] = s_nnz[0];
+    }
+    if (rm <= 0.0) return; // uniform per block
+    // exclusive scan of the per-thread seed counts (thread t owns elements lo+t, lo+t+256, ...)
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        for (int t = 0; t < RED_THREADS; ++t) { const u32 x = s_seed[t]; s_seed[t] = acc; acc += x; }
+        s_base = acc ? atomicAdd(&seed_count[slot], acc) : 0u;
+    }
+    __syncthreads();
+    u64* out = seeds + (size_t)slot * n + s_base + s_seed[threadIdx.x];
+    for (int v = lo + threadIdx.x; v < hi; v += RED_THREADS) {
+        const double r = res[v];
+        if (r > 0.0) {
+            const int32_t d = deg[v];
+            if (d ? (r >= rm * (double)d) : true) *out++ = make_entry(slot, (u32)d, v);
+        }
     }
 }
 __global__ void residue_final_kernel(int nblocks, const double* __restrict__ part_sum, const u32* __restrict__ part_nnz,
