@@ -684,7 +684,16 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
             // (measured: 4 slots 134 q/s without a window vs 90 q/s with deg+offsets pinned).
             const bool fits = ctx->l2_policy && ctx->win_push_bytes <= ctx->l2_persist_max && ctx->win_walk_bytes <= ctx->l2_persist_max;
             if (!fits) ctx->win_push_bytes = ctx->win_walk_bytes = 0;
-            if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, fits ? ctx->l2_persist_max : 0);
+            size_t limit = fits ? ctx->l2_persist_max : 0;
+            if (!fits && ctx->l2_policy && !getenv("FORA_NO_WALK_PIN")) {
+                // many slots: pin only the row offsets (19 MB at LJ scale, read on every hop) during the walks; a small
+                // carve-out costs the push kernel nothing measurable (+3.5 % walk steps/s)
+                ctx->win_walk_off = b_res + b_deg;
+                ctx->win_walk_bytes = b_ptr;
+                limit = std::min(ctx->l2_persist_max, b_ptr + ((size_t)1 << 20));
+                if (ctx->win_walk_bytes > limit) { ctx->win_walk_bytes = 0; limit = 0; }
+            }
+            if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, limit);
         }
         CK(ctx->front0.ensure(fcap));
         CK(ctx->front1.ensure(fcap));
