@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <string>
+#include <functional>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -101,7 +102,8 @@ struct fora_ctx {
     bool trace_on = false;
     DevBuf<PushCtl> ctl;
     DevBuf<SlotMeta> meta;
-    SlotMeta* h_meta = nullptr; // pinned
+    SlotMeta* h_meta = nullptr; // pinned + mapped; h_meta_dev is the device-side alias
+    SlotMeta* h_meta_dev = nullptr;
     DevBuf<double> part_sum;
     DevBuf<u32> part_nnz;
     int red_blocks = 0;
@@ -214,7 +216,8 @@ extern "C" int fora_ctx_create(int device, uint64_t seed, fora_ctx** out) {
         return FORA_ECUDA;
     }
     if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaMallocHost((void**)&ctx->h_meta, sizeof(SlotMeta)) != cudaSuccess) {
+        cudaHostAlloc((void**)&ctx->h_meta, sizeof(SlotMeta), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->h_meta_dev, ctx->h_meta, 0) != cudaSuccess) {
         g_create_error = "stream / pinned allocation failed";
         delete ctx;
         return FORA_ECUDA;
@@ -789,8 +792,17 @@ static int meta_h2d(fora_ctx* ctx) {
     CK(cudaMemcpyAsync(ctx->meta.p, ctx->h_meta, sizeof(SlotMeta), cudaMemcpyHostToDevice, ctx->stream));
     return FORA_OK;
 }
+// The per-round control block goes to the host through a kernel that stores into mapped pinned memory, not through
+// the device->host copy engine: that engine is a FIFO shared by all streams, and a 4 KB control read queued behind
+// the 1.2 GB result copy of the previous wave (copy stream) would stall the next wave for the whole transfer.
+__global__ void meta_out_kernel(const u32* __restrict__ src, u32* __restrict__ dst, int words) {
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
 static int meta_d2h_sync(fora_ctx* ctx) {
-    CK(cudaMemcpyAsync(ctx->h_meta, ctx->meta.p, sizeof(SlotMeta), cudaMemcpyDeviceToHost, ctx->stream));
+    static_assert(sizeof(SlotMeta) % sizeof(u32) == 0, "SlotMeta is copied word-wise");
+    meta_out_kernel<<<1, 256, 0, ctx->stream>>>((const u32*)ctx->meta.p, (u32*)ctx->h_meta_dev, (int)(sizeof(SlotMeta) / sizeof(u32)));
+    CKL();
     CK(cudaStreamSynchronize(ctx->stream));
     kev_harvest(ctx);
     return FORA_OK;
@@ -977,8 +989,10 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
 
 // Walk phase of a wave: plan + walk kernels; ppr is accumulated in place into `ppr` ([slots*n],
 // holding the reserve on entry).  round_tag distinguishes the Philox streams of top-k rounds.
+// groups > 1 launches the walk kernel once per group of slots and calls after_group(lo, hi) behind each launch, so a
+// caller can ship finished slots while the remaining ones still walk.
 static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_zero_hop, u32 round_tag, const u64* idx_used,
-                     u32 part = 0, u32 nparts = 1) {
+                     u32 part = 0, u32 nparts = 1, int groups = 1, const std::function<int(int, int)>& after_group = nullptr) {
     const DeviceGraph& g = ctx->g;
     const int S = ctx->slots;
     SlotMeta* m = ctx->meta.p;
@@ -1013,18 +1027,29 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
         int wrc = set_l2_window(ctx, ctx->win_walk_off, ctx->win_walk_bytes);
         if (wrc) return wrc;
     }
-    kev_begin(ctx, 1);
-    if (g.off32) {
-        CsrView<u32> v{ctx->hot_ptr32, g.out_col};
-        if (no_zero_hop) walk_kernel<u32, true><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
-        else walk_kernel<u32, false><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
-    } else {
-        CsrView<int64_t> v{g.out_ptr64, g.out_col};
-        if (no_zero_hop) walk_kernel<int64_t, true><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
-        else walk_kernel<int64_t, false><<<dim3(wgx, S), WALK_THREADS, 0, ctx->stream>>>(wa, v);
+    groups = std::max(1, std::min(groups, S));
+    for (int gi = 0; gi < groups; ++gi) {
+        const int lo = (int)((long long)S * gi / groups), hi = (int)((long long)S * (gi + 1) / groups);
+        if (hi <= lo) continue;
+        wa.slot0 = lo;
+        const dim3 grid(wgx, hi - lo);
+        kev_begin(ctx, 1);
+        if (g.off32) {
+            CsrView<u32> v{ctx->hot_ptr32, g.out_col};
+            if (no_zero_hop) walk_kernel<u32, true><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            else walk_kernel<u32, false><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+        } else {
+            CsrView<int64_t> v{g.out_ptr64, g.out_col};
+            if (no_zero_hop) walk_kernel<int64_t, true><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            else walk_kernel<int64_t, false><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+        }
+        kev_end(ctx);
+        CKL();
+        if (after_group) {
+            int arc = after_group(lo, hi);
+            if (arc) return arc;
+        }
     }
-    kev_end(ctx);
-    CKL();
     return FORA_OK;
 }
 
@@ -1374,10 +1399,32 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
             h->qid[s] = (u32)(q0 + s);
         }
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
+        // results leave through a staging buffer on a second stream, so the device->host copy of wave w overlaps the
+        // computation of wave w+1 (the slot vectors are re-initialised immediately).  The caller has made sure the
+        // previous wave's copy released the staging buffer.
+        bool shipped = false;
+        auto ship = [&](int lo, int hi) -> int {
+            if (hi <= lo) return FORA_OK;
+            for (int s = lo; s < hi; ++s) {
+                int r2 = vec_to_original(ctx, ctx->reserve.p + n * s, ctx->stage.p + n * s, n); // back to original ids
+                if (r2) return r2;
+            }
+            CK(cudaEventRecord(ctx->ev_stage_ready, ctx->stream));
+            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_ready, 0));
+            CK(cudaMemcpyAsync(ppr + ((size_t)q0 + lo) * n, ctx->stage.p + n * lo, sizeof(double) * n * (size_t)(hi - lo), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CK(cudaEventRecord(ctx->ev_stage_free, ctx->copy_stream));
+            ctx->stage_busy = true;
+            return FORA_OK;
+        };
         if (algo == FORA_ALGO_FORA) {
             if ((rc = push_wave(ctx, cnt, d_sources ? d_sources + q0 : nullptr, fr.data(), rounds.data()))) return rc;
             CK(cudaEventRecord(ctx->ev[2], ctx->stream));
-            if ((rc = walk_wave(ctx, ctx->reserve.p, 0, ctx->p.opt, ctx->p.opt, 0, nullptr))) return rc;
+            if (ppr && S >= 8) { // ship finished slot groups while the others still walk: the exposed copy tail shrinks 4x
+                if (ctx->stage_busy) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
+                CK(ctx->stage.ensure(n * (size_t)S));
+                if ((rc = walk_wave(ctx, ctx->reserve.p, 0, ctx->p.opt, ctx->p.opt, 0, nullptr, 0, 1, 4, [&](int lo, int hi) { return ship(lo, std::min(hi, cnt)); }))) return rc;
+                shipped = true;
+            } else if ((rc = walk_wave(ctx, ctx->reserve.p, 0, ctx->p.opt, ctx->p.opt, 0, nullptr))) return rc;
         } else if (algo == FORA_ALGO_FWDPUSH) { // query.h:1503-1508: push at config.rmax, ppr = reserve
             const int keep = ctx->p.balanced;
             ctx->p.balanced = 0;
@@ -1423,18 +1470,10 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
             CK(cudaMemcpyAsync(ctx->meta.p->nwalk, h->nwalk, sizeof(u64) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
         }
         CK(cudaEventRecord(ctx->ev[3], ctx->stream));
-        if (ppr) {
-            // results leave through a staging buffer on a second stream, so the device->host copy of wave w
-            // overlaps the computation of wave w+1 (the slot vectors are re-initialised immediately)
+        if (ppr && !shipped) {
             CK(ctx->stage.ensure(n * (size_t)S));
             if (ctx->stage_busy) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
-            for (int s = 0; s < cnt; ++s)
-                if ((rc = vec_to_original(ctx, ctx->reserve.p + n * s, ctx->stage.p + n * s, n))) return rc; // back to original ids
-            CK(cudaEventRecord(ctx->ev_stage_ready, ctx->stream));
-            CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_stage_ready, 0));
-            CK(cudaMemcpyAsync(ppr + (size_t)q0 * n, ctx->stage.p, sizeof(double) * n * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
-            CK(cudaEventRecord(ctx->ev_stage_free, ctx->copy_stream));
-            ctx->stage_busy = true;
+            if ((rc = ship(0, cnt))) return rc;
         }
         CK(cudaEventRecord(ctx->ev[4], ctx->stream));
         if ((rc = meta_d2h_sync(ctx))) return rc;

@@ -227,6 +227,7 @@ struct WalkArgs {
     const int32_t* __restrict__ idx_dest;
     const u64* __restrict__ idx_used; // per-round cursor (top-k), may be null
     u32 part, nparts;                 // multi-GPU walk split: this launch walks chunks [part*C/nparts, (part+1)*C/nparts)
+    int slot0;                        // first slot of this launch (blockIdx.y counts from it)
 };
 
 // The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
     __shared__ long long s_rel[WALK_CHUNK + 2];
     __shared__ unsigned short s_own[WALK_CHUNK];
     __shared__ u32 s_next;
-    const int slot = blockIdx.y;
+    const int slot = a.slot0 + (int)blockIdx.y;
     if (a.slot_state[slot] != 1) return;
     const u64 W = a.nwalk[slot];
     if (W == 0) return;
