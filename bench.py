@@ -158,7 +158,7 @@ def run_reference_arm(args):
         cores = sorted(os.sched_getaffinity(0))
     except Exception:
         cores = list(range(os.cpu_count() or 1))
-    P = max(1, min(len(cores), args.ref_procs))
+    P = max(1, min(len(cores), args.ref_procs if args.ref_procs > 0 else len(cores)))
     per_step = P * args.ref_queries_per_proc  # queries per step, one worker process per core
     ctx = mp.get_context("fork")
     budget = float(os.environ.get("FORA_REF_BUDGET_S", "600"))
@@ -189,7 +189,7 @@ def run_reference_arm(args):
     value = per_step * args.steps / total
     out = {
         "impl": "reference", "metric": "SSPPR queries/s (FORA eps=0.5, LJ-shape)", "value": value, "unit": "queries/s",
-        "n_gpus": 0, "steps": args.steps, "warmup": args.warmup, "warmup_run": warm_done, "ms_per_step": 1e3 * total / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "warmup_run": warm_done, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "%s; FORA eps=0.5 --balanced --opt; %d queries per step (one per host core)" % (desc, per_step),
                    "shape": shape, "queries_per_step": per_step},
@@ -215,7 +215,7 @@ def main():
     ap.add_argument("--slots", type=int, default=int(os.environ.get("FORA_SLOTS", "32")))
     ap.add_argument("--e2e-queries", type=int, default=128)
     ap.add_argument("--cpu-sample", type=int, default=1, help="queries timed on the CPU baseline (0 = skip)")
-    ap.add_argument("--ref-procs", type=int, default=16)
+    ap.add_argument("--ref-procs", type=int, default=0, help="worker processes of the reference arm (0 = one per host core)")
     ap.add_argument("--ref-queries-per-proc", type=int, default=1)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
