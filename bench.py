@@ -233,6 +233,8 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
     torch.cuda.set_device(local)
+    from fora_b200 import shard
+    numa = shard.bind_to_gpu_numa_node(local) if world > 1 and not os.environ.get("FORA_NO_NUMA_BIND") else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n, m, desc, op, oc, _, _ = make_graph(args.shape)
@@ -246,7 +248,6 @@ def main():
 
     B = args.batch
     # weak scaling: every rank processes B queries per step, its own shard of a world*B global batch
-    from fora_b200 import shard
 
     def step_ids(i):
         return shard.step_query_ids(queries, i, B, rank, world)[0]
@@ -331,7 +332,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "%s; FORA eps=0.5 --balanced --opt, %d batched queries per step per GPU from a %d-query list" % (desc, B, N_QUERIES),
-                       "shape": args.shape, "queries_per_step_per_gpu": B, "slots": args.slots, "parallelism": "query-sharded x%d, graph replicated" % world,
+                       "shape": args.shape, "queries_per_step_per_gpu": B, "slots": args.slots, "parallelism": "query-sharded x%d, graph replicated" % world, "numa_node_rank0": numa,
                        "l2": "inputs larger than L2 (CSR 0.33 GB + 39 MB dense state per query re-initialised every query)",
                        "rmax": rmax, "omega": omega},
             "clocks": clocks,

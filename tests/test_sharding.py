@@ -71,3 +71,16 @@ def test_balanced_ranges_edge_cases():
         assert cuts[0] == 0 and cuts[-1] == 7 and len(cuts) == w + 1 and all(cuts[i] <= cuts[i + 1] for i in range(w))
     ids, keys = shard.step_query_ids(np.arange(10), step=7, batch=4, rank=1, world=2)
     assert keys.tolist() == [(7 * 8 + 4 + j) % 10 for j in range(4)]
+
+
+def test_numa_binding_helper_is_safe_without_a_gpu():
+    from fora_b200 import shard
+    assert shard._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert shard._parse_cpulist("") == set()
+    before = os.sched_getaffinity(0)
+    node = shard.bind_to_gpu_numa_node(0)   # no NVML device here: must be a no-op
+    if node is None:
+        assert os.sched_getaffinity(0) == before
+    else:
+        assert os.sched_getaffinity(0) <= before
+        os.sched_setaffinity(0, before)
