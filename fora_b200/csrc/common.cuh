@@ -35,6 +35,9 @@ struct DeviceGraph {
     u32* out_ptr32 = nullptr;
     int32_t* out_col = nullptr;
     int32_t* deg = nullptr; // out-degree
+    // push kernel only: out_col with the target's out-degree packed into the id's spare high bits (engine.cu pack_columns)
+    int32_t* out_colx = nullptr;
+    u32 deg_shift = 0;
     int64_t* in_ptr64 = nullptr;
     u32* in_ptr32 = nullptr;
     int32_t* in_col = nullptr;

@@ -228,6 +228,7 @@ struct WalkArgs {
     const u64* __restrict__ idx_used; // per-round cursor (top-k), may be null
     u32 part, nparts;                 // multi-GPU walk split: this launch walks chunks [part*C/nparts, (part+1)*C/nparts)
     int slot0;                        // first slot of this launch (blockIdx.y counts from it)
+    u64 hot_elems;                    // HINT instantiation: neighbour slots below this position are kept in L2 (evict_last), the rest stream through
 };
 
 // The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
@@ -240,7 +241,7 @@ struct WalkArgs {
 // finishes a walk immediately starts the next one, so neither the longest walk of a warp nor the tail of
 // a chunk idles lanes -- and advance two steps per Philox block, so the RNG is evaluated by all lanes in
 // lockstep (one Philox4x32-10 block = stop/pick, stop/pick).
-template <typename OffT, bool NO_ZERO_HOP>
+template <typename OffT, bool NO_ZERO_HOP, bool HINT>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<OffT> g) {
     __shared__ long long s_rel[WALK_CHUNK + 2];
     __shared__ unsigned short s_own[WALK_CHUNK];
@@ -257,6 +258,12 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
     double* ppr = a.ppr + (size_t)slot * a.n;
     const u32 k0 = a.seed_lo ^ (a.qid[slot] * 0x9E3779B9u), k1 = a.seed_hi ^ a.round_tag;
     u64 my_hops = 0, my_hits = 0;
+    // HINT: the L2 as a static cache of the hot prefix of the column array (LRU lets the once-touched cold slots evict it)
+    u64 pol_keep = 0, pol_stream = 0;
+    if (HINT) {
+        pol_keep = l2_policy_evict_last();
+        pol_stream = l2_policy_evict_first();
+    }
 
     const u64 chunk_lo = a.nparts > 1 ? nchunks * a.part / a.nparts : 0;
     const u64 chunk_hi = a.nparts > 1 ? nchunks * (a.part + 1) / a.nparts : nchunks;
@@ -335,7 +342,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
                 const OffT b = g.ptr[cur];
                 const u32 d = (u32)(g.ptr[cur + 1] - b);
                 if (d) {
-                    cur = __ldg(&g.col[b + (OffT)__umulhi(r_pick, d)]); // algo.h:135-136
+                    const OffT pos = b + (OffT)__umulhi(r_pick, d); // algo.h:135-136
+                    cur = HINT ? ld_s32_hint(&g.col[pos], (u64)pos < a.hot_elems ? pol_keep : pol_stream) : __ldg(&g.col[pos]);
                     ++my_hops;
                 } else {
                     cur = start; // algo.h:138-140

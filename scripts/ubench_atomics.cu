@@ -1,3 +1,4 @@
+#include <string.h>
 // Microbenchmark (development aid): throughput of random fp64 atomics on B200.
 #include <cstdio>
 #include <cstdint>
@@ -25,9 +26,22 @@ template<int MODE> void run(const char* name, double* a, int* deg, uint32_t n, u
   cudaEventRecord(e0); k<MODE><<<grid,block>>>(a,deg,n,total,sink,ctr); cudaEventRecord(e1); cudaEventSynchronize(e1);
   float ms; cudaEventElapsedTime(&ms,e0,e1); printf("%-28s n=%9u (%6.1f MB) grid=%d x %d : %8.2f G ops/s\n", name, n, n*8.0/1e6, grid, block, total/ms/1e6);
 }
-int main(){ double* a; int* deg; double* sink; unsigned* ctr; uint32_t nmax=80000000; cudaMalloc(&a, nmax*8ull); cudaMalloc(&deg,nmax*4ull); cudaMalloc(&sink,8); cudaMalloc(&ctr,4);
+int main(int argc, char** argv){ double* a; int* deg; double* sink; unsigned* ctr; uint32_t nmax=80000000; cudaMalloc(&a, nmax*8ull); cudaMalloc(&deg,nmax*4ull); cudaMalloc(&sink,8); cudaMalloc(&ctr,4);
   cudaMemset(a,0,nmax*8ull); cudaMemset(deg,1,nmax*4ull); cudaMemset(ctr,0,4);
   u64 total = 1ull<<30;
+  // argv[1] = "gran": only the L2 fill-granularity comparison (cudaLimitMaxL2FetchGranularity 32 / 64 / 128 bytes)
+  if (argc > 1 && !strcmp(argv[1], "gran")) {
+    for (size_t gran : {(size_t)64, (size_t)32, (size_t)128, (size_t)64}) {
+      cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+      printf("== cudaLimitMaxL2FetchGranularity set %zu -> %s, now %zu\n", gran, cudaGetErrorString(e), got);
+      for (uint32_t n : {4847571u*4, 4847571u*16}) {
+        run<0>("ATOM.f64 (return)",a,deg,n,total,sink,ctr,296,512);
+        run<2>("LDG.64 random",a,deg,n,total,sink,ctr,296,512);
+        run<3>("ATOM.f64 + LDG deg",a,deg,n,total,sink,ctr,296,512);
+      }
+    }
+    return 0;
+  }
   for (uint32_t n : {4847571u, 4847571u*4, 4847571u*16}) {
     for (int grid : {148*2, 148*8}) { int block = grid==296?512:256;
       run<0>("ATOM.f64 (return)",a,deg,n,total,sink,ctr,grid,block);
