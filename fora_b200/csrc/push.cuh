@@ -102,7 +102,7 @@ struct PushSmem {
     OffT beg[PUSH_BATCH];
     int slot[PUSH_BATCH];        // slot, or ~slot when the entry is dangling
     u64 wqueue[PUSH_WARPS][PUSH_WQ]; // crossing vertices, one private queue per warp (no shared atomics)
-    u64 warp_tot[PUSH_WARPS];
+    u64 warp_tot[2][PUSH_WARPS]; // double-buffered by batch parity: one CTA barrier per scan
     double rmax[MAX_SLOTS];
     int32_t source[MAX_SLOTS];
     u32 cnt_edges[MAX_SLOTS], cnt_verts[MAX_SLOTS];
@@ -141,22 +141,20 @@ __device__ __forceinline__ int32_t ld_col_stream(const int32_t* addr, u64 policy
     return v;
 }
 
-// block-wide inclusive scan of one u64 per thread; returns the inclusive value, *total = block sum
+// block-wide inclusive scan of one u64 per thread; returns the inclusive value, *total = block sum.  One CTA
+// barrier per call: the warp totals go to buffer `buf` (callers alternate 0/1), every warp scans the 16 totals itself,
+// and the next call writes the other buffer, so a slow reader of this one is never overtaken.
 template <typename OffT>
-__device__ __forceinline__ u64 block_incl_scan(PushSmem<OffT>& sm, u64 v, u64* total) {
+__device__ __forceinline__ u64 block_incl_scan(PushSmem<OffT>& sm, u64 v, u64* total, int buf) {
     const int lane = lane_id(), w = threadIdx.x >> 5;
     u64 incl = warp_incl_scan64(v);
-    if (lane == 31) sm.warp_tot[w] = incl;
+    if (lane == 31) sm.warp_tot[buf][w] = incl;
     __syncthreads();
-    if (w == 0) {
-        u64 t = lane < PUSH_WARPS ? sm.warp_tot[lane] : 0;
-        const u64 ti = warp_incl_scan64(t);
-        if (lane < PUSH_WARPS) sm.warp_tot[lane] = ti; // inclusive over warps
-    }
-    __syncthreads();
-    *total = sm.warp_tot[PUSH_WARPS - 1];
-    if (w > 0) incl += sm.warp_tot[w - 1];
-    __syncthreads();
+    const u64 t = lane < PUSH_WARPS ? sm.warp_tot[buf][lane] : 0;
+    const u64 ti = warp_incl_scan64(t); // inclusive over warps
+    *total = __shfl_sync(FULL, ti, PUSH_WARPS - 1);
+    const u64 before = __shfl_sync(FULL, ti, w > 0 ? w - 1 : 0);
+    if (w > 0) incl += before;
     return incl;
 }
 
@@ -183,6 +181,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
     const u32 cs = (nf + count - 1) / count;
     const u32 lo_i = min(nf, rank * cs), hi_i = min(nf, lo_i + cs);
     u64 carry = 0;
+    int parity = 0;
     for (u32 b0 = lo_i; b0 < hi_i; b0 += PUSH_THREADS * PUSH_UA) {
         const u32 i0 = b0 + threadIdx.x * PUSH_UA;
         u64 e[PUSH_UA];
@@ -237,7 +236,8 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
                 }
         }
         u64 total;
-        const u64 incl = block_incl_scan(sm, (u64)esum, &total);
+        const u64 incl = block_incl_scan(sm, (u64)esum, &total, parity);
+        parity ^= 1;
         const u32 tbase = (u32)(carry + incl - esum);
 #pragma unroll
         for (int k = 0; k < PUSH_UA; ++k)
@@ -245,7 +245,8 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
         carry += total;
     }
     if (threadIdx.x == 0) a.block_sum[rank] = carry;
-    // flush the per-slot counters of this CTA (block_incl_scan's barriers ordered the shared atomics)
+    // flush the per-slot counters of this CTA once all its warps are past their last shared atomics
+    __syncthreads();
     if (lo_i < hi_i && threadIdx.x < (u32)a.slots) {
         const int sl = threadIdx.x;
         const u32 v = sm.cnt_verts[sl];
@@ -310,6 +311,9 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
     u32 wq = 0;       // entries in this warp's queue (warp-uniform register)
     int wq_slot = 0;  // the slot they belong to
     u64* myq = sm.wqueue[w];
+    // (Rejected after measurement: tiles claimed dynamically from a cursor with guided, shrinking sizes -- 16.7 instead
+    // of 18.4 G edges/s; a tile start costs a 32-ary search in global memory plus a full batch staging, so fewer,
+    // larger static tiles win although the grid barrier then waits for the CTAs that drew one tile more.)
     for (u64 lo = (u64)rank * T; lo < E; lo += (u64)count * T) {
         const u64 hi = min(E, lo + T);
         // first entry of the tile: largest i with G(i) <= lo, G(i) = base[i / cs] + eoff[i]
@@ -472,13 +476,15 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
 
     for (u32 level = 0;; ++level) {
         // the level's frontier: per-slot segments concatenated in slot order
-        if (threadIdx.x == 0) {
-            u32 acc = 0;
-            for (int s = 0; s < a.slots; ++s) {
-                sm.fbase[s] = acc;
-                acc += *((volatile u32*)&ctl->fcount[level % 3][s]);
-            }
-            sm.fbase[a.slots] = acc;
+        if (threadIdx.x < WARP) { // exclusive scan of the (<= 64) per-slot counts by one warp
+            const int l = threadIdx.x;
+            const u32 c0 = l < a.slots ? *((volatile u32*)&ctl->fcount[level % 3][l]) : 0u;
+            const u32 c1 = l + WARP < a.slots ? *((volatile u32*)&ctl->fcount[level % 3][l + WARP]) : 0u;
+            const u32 i0 = warp_incl_scan(c0);
+            const u32 i1 = warp_incl_scan(c1) + __shfl_sync(FULL, i0, 31);
+            if (l < a.slots) sm.fbase[l] = i0 - c0;
+            if (l + WARP < a.slots) sm.fbase[l + WARP] = i1 - c1;
+            if (l == 31) sm.fbase[a.slots] = i1;
         }
         __syncthreads();
         const u32 nf = sm.fbase[a.slots];

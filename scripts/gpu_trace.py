@@ -30,3 +30,8 @@ for i in range(lv):
     tot += dt
     print("L%3d nf=%8d E=%9d  level %8.1f us  phaseA %7.1f us  -> %6.2f G edges/s" % (i, t[i, 1], t[i, 2], dt / 1e3, da / 1e3, t[i, 2] / max(dt, 1)))
 print("sum %.1f us" % (tot / 1e3))
+A = sum((t[i, 3] - t[i, 0]) for i in range(lv - 1)) / 1e3
+L = sum((t[i + 1, 0] - t[i, 0]) for i in range(lv - 1)) / 1e3
+small = sum((t[i + 1, 0] - t[i, 0]) for i in range(lv - 1) if t[i, 2] < 2000000) / 1e3
+print("phase A %.1f us (%.0f %%), phase B + barriers %.1f us, levels with < 2M edges: %.1f us (%.0f %%), entries %d edges %d" % (
+    A, 100 * A / L, L - A, small, 100 * small / L, t[:, 1].sum(), t[:, 2].sum()))

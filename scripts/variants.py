@@ -21,7 +21,8 @@ import fora_b200 as fb  # noqa: E402
 SLOTS = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 NQ = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 KNOBS = ("FORA_L2_FETCH", "FORA_PUSH_PACK", "FORA_RELABEL_KEY", "FORA_WALK_HOT_MB", "FORA_L2_HINTS", "FORA_NO_WALK_PIN",
-         "FORA_COST_WALK", "FORA_COST_EDGE", "FORA_COST_VERTEX", "FORA_TILE_MAX", "FORA_WALK_GRID")
+         "FORA_COST_WALK", "FORA_COST_EDGE", "FORA_COST_VERTEX", "FORA_TILE_MAX", "FORA_WALK_GRID", "FORA_WALK_V", "FORA_WALK_HOT_KEEP",
+         "FORA_PUSH_V", "FORA_PUSH_DYN")
 
 n, m = 4847571, 68993773
 t0 = time.time()
@@ -98,8 +99,17 @@ elif PLAN == "b":
     env = group("tiles / walk grid", env, [("tile 64K", {"FORA_TILE_MAX": 65536}), ("tile 128K", {"FORA_TILE_MAX": 131072}),
                                            ("walk grid x8", {"FORA_WALK_GRID": 8}), ("walk grid x32", {"FORA_WALK_GRID": 32})])
     env = group("extra", env, [(k, json.loads(v)) for k, v in (a.split("=", 1) for a in sys.argv[4:])])
+elif PLAN == "c":
+    env = group("walk loop", env, [("walk v2 (warp-converged)", {"FORA_WALK_V": 2})])
+    env = group("walk: cold column slots evict_first", env, [("cold beyond %d MB" % mb, {"FORA_WALK_HOT_MB": mb}) for mb in (4, 8, 16, 32, 64, 128)])
+    env = group("extra", env, [(k, json.loads(v)) for k, v in (a.split("=", 1) for a in sys.argv[4:])])
+elif PLAN == "d":
+    env = group("push: dynamic guided tiles", env, [("dyn 32K", {"FORA_PUSH_DYN": 1}), ("dyn 16K", {"FORA_PUSH_DYN": 1, "FORA_TILE_MAX": 16384}),
+                                                    ("dyn 64K", {"FORA_PUSH_DYN": 1, "FORA_TILE_MAX": 65536}),
+                                                    ("dyn 8K", {"FORA_PUSH_DYN": 1, "FORA_TILE_MAX": 8192})])
+    env = group("extra", env, [(k, json.loads(v)) for k, v in (a.split("=", 1) for a in sys.argv[4:])])
 print("-- slots", flush=True)
-for s in (16, 24, 40, 48, 56, 64):
+for s in ((16, 24, 40, 48, 56, 64) if PLAN in "ab" else (56,)):
     measure("slots %d" % s, env, slots=s)
 print("FINAL", json.dumps(env), flush=True)
 
