@@ -1071,6 +1071,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     // neighbour slots beyond the first 32 MB of the (hot-first) column array stream through the L2 with evict_first
     // (measured: 16..64 MB within 1 %, +2.6 % hops/s over no hint)
     wa.hot_elems = (u64)((getenv("FORA_WALK_HOT_MB") ? atof(getenv("FORA_WALK_HOT_MB")) : 32.0) * 262144.0);
+    wa.debug_no_red = getenv("FORA_DEBUG_NO_RED") ? atoi(getenv("FORA_DEBUG_NO_RED")) : 0;
     wa.hot_keep = getenv("FORA_WALK_HOT_KEEP") ? atoi(getenv("FORA_WALK_HOT_KEEP")) : 0;
     const int wgx = ctx->num_sms * (getenv("FORA_WALK_GRID") ? atoi(getenv("FORA_WALK_GRID")) : 16);
     if (ppr == ctx->reserve.p) {

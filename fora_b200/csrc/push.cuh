@@ -31,9 +31,9 @@ constexpr int MAX_PUSH_CTAS = 512;
 constexpr u32 TILE_MIN = 2048;   // smallest edge range worth giving to a CTA
 constexpr u32 TILE_MAX = 32768;  // tiles of a large level: the grid sweeps the edge line 296*32K edges at a time (16K: -2.8 % edges/s, 8K: -7 %)
 #ifndef CFG_PUSH_UA
-#define CFG_PUSH_UA 4
+#define CFG_PUSH_UA 1
 #endif
-constexpr int PUSH_UA = CFG_PUSH_UA;       // frontier entries per thread per phase-A batch
+constexpr int PUSH_UA = CFG_PUSH_UA;       // frontier entries per thread per phase-A batch (measured 1: 19.2, 2: 18.9, 4: 18.5, 8: 16.6 G edges/s)
 #ifndef CFG_PUSH_BATCH
 #define CFG_PUSH_BATCH 1024
 #endif

@@ -229,6 +229,7 @@ struct WalkArgs {
     u32 part, nparts;                 // multi-GPU walk split: this launch walks chunks [part*C/nparts, (part+1)*C/nparts)
     int slot0;                        // first slot of this launch (blockIdx.y counts from it)
     u64 hot_elems;                    // HINT instantiation: neighbour slots from this position on are loaded with L2 evict_first
+    int debug_no_red;                 // development ablation only (FORA_DEBUG_NO_RED): skip the ppr accumulation, results are WRONG
     int hot_keep;                     // 1: the slots below hot_elems are additionally loaded with evict_last (measured worse: they
                                       //    compete with the pinned row offsets for the persisting carve-out)
 };
@@ -438,7 +439,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel2(WalkArgs a, CsrView
                 }
                 if (!done && (u32)(g.ptr[v + 1] - g.ptr[v]) == 0) done = true; // algo.h:127-129
                 if (done) {
-                    atomicAdd(&ppr[dest], inc);
+                    if (!a.debug_no_red) atomicAdd(&ppr[dest], inc);
                 } else {
                     cur = start = v;
                     jlo = (u32)j;
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel2(WalkArgs a, CsrView
                     const u32 r_stop = half ? rnd.z : rnd.x;
                     const u32 r_pick = half ? rnd.w : rnd.y;
                     if (!first && r_stop < a.alpha_thr) { // algo.h:131-133
-                        atomicAdd(&ppr[cur], inc);
+                        if (!a.debug_no_red) atomicAdd(&ppr[cur], inc);
                         have = false;
                         break;
                     }

@@ -17,6 +17,7 @@ template<int MODE> __global__ void k(double* a, const int* deg, uint32_t n, u64 
     else if(MODE==6) { acc += atomicAdd((float*)&a[j], 1e-9f); } // f32 ATOM
     else if(MODE==7) { atomicAdd(ctr, 1u); } // same-address RED u32
     else if(MODE==8) { acc += atomicAdd(ctr, 1u); } // same-address ATOM u32 (per thread)
+    else if(MODE==9) { acc += __ldg(&((const int*)a)[j]); } // random 4B load (n counts ints)
   }
   if(acc==123.456) *sink=acc;
 }
@@ -30,6 +31,11 @@ int main(int argc, char** argv){ double* a; int* deg; double* sink; unsigned* ct
   cudaMemset(a,0,nmax*8ull); cudaMemset(deg,1,nmax*4ull); cudaMemset(ctr,0,4);
   u64 total = 1ull<<30;
   // argv[1] = "gran": only the L2 fill-granularity comparison (cudaLimitMaxL2FetchGranularity 32 / 64 / 128 bytes)
+  if (argc > 1 && !strcmp(argv[1], "rand4")) { // random 4-byte reads: the neighbour fetch of a walk without the dependency chain
+    for (uint32_t n : {16u<<20, 32u<<20, 69000000u, 138000000u})
+      for (int grid : {148*8, 148*16}) run<9>("LDG.32 random (n ints)",a,deg,n,total,sink,ctr,grid,256);
+    return 0;
+  }
   if (argc > 1 && !strcmp(argv[1], "gran")) {
     for (size_t gran : {(size_t)64, (size_t)32, (size_t)128, (size_t)64}) {
       cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran); size_t got = 0; cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);

@@ -18,11 +18,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import fora_b200 as fb  # noqa: E402
 
+if os.environ.get("FORA_VARIANT_LIB"):  # a build with other compile-time constants (fora_b200/variants/lib_<name>.so)
+    fb.LIB_PATH = os.path.join(ROOT, "fora_b200", "variants", "lib_%s.so" % os.environ["FORA_VARIANT_LIB"])
+    print("library:", fb.LIB_PATH, flush=True)
+
 SLOTS = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 NQ = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 KNOBS = ("FORA_L2_FETCH", "FORA_PUSH_PACK", "FORA_RELABEL_KEY", "FORA_WALK_HOT_MB", "FORA_L2_HINTS", "FORA_NO_WALK_PIN",
          "FORA_COST_WALK", "FORA_COST_EDGE", "FORA_COST_VERTEX", "FORA_TILE_MAX", "FORA_WALK_GRID", "FORA_WALK_V", "FORA_WALK_HOT_KEEP",
-         "FORA_PUSH_V", "FORA_PUSH_DYN")
+         "FORA_PUSH_V", "FORA_PUSH_DYN", "FORA_DEBUG_NO_RED", "FORA_WALK_PIN_PPR")
 
 n, m = 4847571, 68993773
 t0 = time.time()
@@ -102,6 +106,11 @@ elif PLAN == "b":
 elif PLAN == "c":
     env = group("walk loop", env, [("walk v2 (warp-converged)", {"FORA_WALK_V": 2})])
     env = group("walk: cold column slots evict_first", env, [("cold beyond %d MB" % mb, {"FORA_WALK_HOT_MB": mb}) for mb in (4, 8, 16, 32, 64, 128)])
+    env = group("extra", env, [(k, json.loads(v)) for k, v in (a.split("=", 1) for a in sys.argv[4:])])
+elif PLAN == "m":  # one measurement of the defaults (used to compare variant libraries)
+    measure("defaults", env)
+    sys.exit(0)
+elif PLAN == "x":  # extras only
     env = group("extra", env, [(k, json.loads(v)) for k, v in (a.split("=", 1) for a in sys.argv[4:])])
 elif PLAN == "d":
     env = group("push: dynamic guided tiles", env, [("dyn 32K", {"FORA_PUSH_DYN": 1}), ("dyn 16K", {"FORA_PUSH_DYN": 1, "FORA_TILE_MAX": 16384}),
