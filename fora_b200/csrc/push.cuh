@@ -202,6 +202,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             }
         }
         u32 esum = 0, vcnt = 0, dsum = 0;
+        u32 loc[PUSH_UA];
         int slot_first = -1;
         bool same = true;
 #pragma unroll
@@ -212,7 +213,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             a.residue[gi] = 0.0;
             a.reserve[gi] = rs[k] + r[k] * a.alpha;
             a.inc[i0 + k] = d[k] ? ((1.0 - a.alpha) * r[k]) / (double)d[k] : r[k] * (1.0 - a.alpha);
-            a.eoff[i0 + k] = esum; // thread-local exclusive offset, completed below
+            loc[k] = esum; // thread-local exclusive offset, completed below
             esum += d[k] ? d[k] : 1u;
             dsum += d[k];
             ++vcnt;
@@ -241,7 +242,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
         const u32 tbase = (u32)(carry + incl - esum);
 #pragma unroll
         for (int k = 0; k < PUSH_UA; ++k)
-            if (e[k] != ~0ull) a.eoff[i0 + k] += tbase;
+            if (e[k] != ~0ull) a.eoff[i0 + k] = loc[k] + tbase;
         carry += total;
     }
     if (threadIdx.x == 0) a.block_sum[rank] = carry;

@@ -417,7 +417,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel2(WalkArgs a, CsrView
         for (;;) {
             __syncwarp();
             while (!have && more) { // refill; a walk resolved without walking (index hit / dangling start) fetches again
-                const u32 x = atomicAdd(&s_next, 1u);
+                const u32 x = atomicAdd(&s_next, 1u); // (one aggregated atomic per refilling warp measured 2.5 % slower)
                 if (x >= nw) {
                     more = false;
                     break;
