@@ -1072,7 +1072,6 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     // (measured: 16..64 MB within 1 %, +2.6 % hops/s over no hint)
     wa.hot_elems = (u64)((getenv("FORA_WALK_HOT_MB") ? atof(getenv("FORA_WALK_HOT_MB")) : 32.0) * 262144.0);
     wa.debug_no_red = getenv("FORA_DEBUG_NO_RED") ? atoi(getenv("FORA_DEBUG_NO_RED")) : 0;
-    wa.hot_keep = getenv("FORA_WALK_HOT_KEEP") ? atoi(getenv("FORA_WALK_HOT_KEEP")) : 0;
     const int wgx = ctx->num_sms * (getenv("FORA_WALK_GRID") ? atoi(getenv("FORA_WALK_GRID")) : 16);
     if (ppr == ctx->reserve.p) {
         int wrc = set_l2_window(ctx, ctx->win_walk_off, ctx->win_walk_bytes);
@@ -1087,16 +1086,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
         kev_begin(ctx, 1);
         if (g.off32) {
             CsrView<u32> v{ctx->hot_ptr32, g.out_col};
-            const int wv = getenv("FORA_WALK_V") ? atoi(getenv("FORA_WALK_V")) : 2;
-            if (wv == 2) {
-                if (wa.hot_elems) {
-                    if (no_zero_hop) walk_kernel2<u32, true, true><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
-                    else walk_kernel2<u32, false, true><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
-                } else {
-                    if (no_zero_hop) walk_kernel2<u32, true, false><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
-                    else walk_kernel2<u32, false, false><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
-                }
-            } else if (wa.hot_elems) {
+            if (wa.hot_elems && wa.hot_elems < (u64)g.n_edges) {
                 if (no_zero_hop) walk_kernel<u32, true, true><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
                 else walk_kernel<u32, false, true><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
             } else {

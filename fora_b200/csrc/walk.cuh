@@ -21,9 +21,12 @@ namespace fora {
 constexpr int PLAN_THREADS = 1024;
 constexpr int WALK_THREADS = 256;
 #ifndef CFG_WALK_CHUNK
-#define CFG_WALK_CHUNK 1024
+#define CFG_WALK_CHUNK 3840
 #endif
-constexpr int WALK_CHUNK = CFG_WALK_CHUNK; // walks per chunk (4 per thread; 1024 measured best on B200: less shared memory leaves more L1)
+// walks per chunk.  4 bytes of shared memory per walk; 8 resident CTAs x 3840 walks stay inside the 132 KB shared-memory
+// carve-out (124 KB of L1 left).  Larger chunks = fewer chunk tails (lanes idle while the longest walks of a chunk
+// finish): 1024: 98.6, 2048: 108.6, 2560: 110.9, 3840: 113.6, 4608 (next carve-out step): 102.3 G hops/s.
+constexpr int WALK_CHUNK = CFG_WALK_CHUNK;
 
 struct PlanArgs {
     int32_t n;
@@ -230,8 +233,6 @@ struct WalkArgs {
     int slot0;                        // first slot of this launch (blockIdx.y counts from it)
     u64 hot_elems;                    // HINT instantiation: neighbour slots from this position on are loaded with L2 evict_first
     int debug_no_red;                 // development ablation only (FORA_DEBUG_NO_RED): skip the ppr accumulation, results are WRONG
-    int hot_keep;                     // 1: the slots below hot_elems are additionally loaded with evict_last (measured worse: they
-                                      //    compete with the pinned row offsets for the persisting carve-out)
 };
 
 // The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
@@ -241,136 +242,23 @@ struct WalkArgs {
 // Per CTA chunk of WALK_CHUNK walks: (1) the prefix of the sources touching the chunk is staged in shared
 // memory, (2) a divergence-free expansion pass resolves the owner source of every walk of the chunk
 // (binary search, all lanes busy), (3) lanes fetch walks dynamically from a shared counter -- a lane that
-// finishes a walk immediately starts the next one, so neither the longest walk of a warp nor the tail of
-// a chunk idles lanes -- and advance two steps per Philox block, so the RNG is evaluated by all lanes in
-// lockstep (one Philox4x32-10 block = stop/pick, stop/pick).
+// finishes a walk immediately starts the next one -- and advance two steps per Philox block (one
+// Philox4x32-10 block = stop/pick, stop/pick).
+//
+// The loop is warp-converged: every iteration starts at an explicit reconvergence point, the lanes without a walk
+// refill together, and then ALL lanes evaluate one Philox block and up to two steps together; a lane leaves the loop
+// only when the whole warp has nothing left in this chunk.  (The first version let a lane that finished a walk go its
+// own way -- fetch, next Philox block -- while its warp-mates were still stepping, and the warp never met again:
+// 13.7 of 32 lanes active per issued instruction, 89 G hops/s; converged: 18.9 lanes, 97 G hops/s.)
+// HINT: neighbour slots at positions >= hot_elems of the (hot-first) column array are loaded with L2 evict_first.
 template <typename OffT, bool NO_ZERO_HOP, bool HINT>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<OffT> g) {
-    __shared__ long long s_rel[WALK_CHUNK + 2];
-    __shared__ unsigned short s_own[WALK_CHUNK];
-    __shared__ u32 s_next;
-    const int slot = a.slot0 + (int)blockIdx.y;
-    if (a.slot_state[slot] != 1) return;
-    const u64 W = a.nwalk[slot];
-    if (W == 0) return;
-    const u64 nchunks = (W + WALK_CHUNK - 1) / WALK_CHUNK;
-    const int32_t* __restrict__ srcs = a.srcs + (size_t)slot * a.n;
-    const u64* __restrict__ woff = a.woff + (size_t)slot * (a.n + 1);
-    const double* __restrict__ incs = a.incs + (size_t)slot * a.n;
-    const u32* __restrict__ cfirst = a.chunk_first + (size_t)slot * a.chunk_cap;
-    double* ppr = a.ppr + (size_t)slot * a.n;
-    const u32 k0 = a.seed_lo ^ (a.qid[slot] * 0x9E3779B9u), k1 = a.seed_hi ^ a.round_tag;
-    u64 my_hops = 0, my_hits = 0;
-    // HINT: the L2 as a static cache of the hot prefix of the column array (LRU lets the once-touched cold slots evict it)
-    u64 pol_keep = 0, pol_stream = 0;
-    if (HINT) {
-        pol_keep = l2_policy_evict_last();
-        pol_stream = l2_policy_evict_first();
-    }
-
-    const u64 chunk_lo = a.nparts > 1 ? nchunks * a.part / a.nparts : 0;
-    const u64 chunk_hi = a.nparts > 1 ? nchunks * (a.part + 1) / a.nparts : nchunks;
-    for (u64 chunk = chunk_lo + blockIdx.x; chunk < chunk_hi; chunk += gridDim.x) {
-        const u64 w0 = chunk * WALK_CHUNK;
-        const u32 nw = (u32)(min(W, w0 + (u64)WALK_CHUNK) - w0);
-        const u32 s_lo = cfirst[chunk], s_hi = cfirst[chunk + 1];
-        const u32 cnt = s_hi - s_lo + 1; // sources touching this chunk, <= WALK_CHUNK + 1
-        __syncthreads();
-        for (u32 i = threadIdx.x; i <= cnt; i += WALK_THREADS) s_rel[i] = (long long)woff[s_lo + i] - (long long)w0;
-        if (threadIdx.x == 0) s_next = 0;
-        __syncthreads();
-        // expansion: owner of walk x = last i in [0,cnt) with s_rel[i] <= x
-        for (u32 x = threadIdx.x; x < nw; x += WALK_THREADS) {
-            u32 lo = 0, hi = cnt;
-            while (hi - lo > 1) {
-                const u32 mid = (lo + hi) >> 1;
-                if (s_rel[mid] <= (long long)x) lo = mid;
-                else hi = mid;
-            }
-            s_own[x] = (unsigned short)lo;
-        }
-        __syncthreads();
-
-        int32_t cur = 0, start = 0;
-        u32 jlo = 0, jhi = 0, blk = 0;
-        double inc = 0.0;
-        bool have = false, first = false;
-        for (;;) {
-            if (!have) { // fetch the next walk of the chunk
-                const u32 x = atomicAdd(&s_next, 1u);
-                if (x < nw) {
-                    const u32 own = s_own[x];
-                    const u64 j = (u64)((long long)x - s_rel[own]);
-                    const int32_t v = srcs[s_lo + own];
-                    inc = incs[s_lo + own];
-                    bool done = false;
-                    int32_t dest = v;
-                    if (a.with_idx) { // query.h:290-307: the first min(n_v, count) walks come from the index
-                        const u64 used = a.idx_used ? a.idx_used[(size_t)slot * a.n + v] : 0;
-                        const u64 avail = a.idx_cnt[v] - used;
-                        if (j < avail) {
-                            dest = a.idx_dest[a.idx_off[v] + used + j];
-                            done = true;
-                            ++my_hits;
-                        }
-                    }
-                    if (!done && (u32)(g.ptr[v + 1] - g.ptr[v]) == 0) done = true; // algo.h:127-129
-                    if (done) {
-                        atomicAdd(&ppr[dest], inc);
-                    } else {
-                        cur = start = v;
-                        jlo = (u32)j;
-                        jhi = (u32)(j >> 32);
-                        blk = 0;
-                        first = NO_ZERO_HOP;
-                        have = true;
-                    }
-                } else {
-                    break; // chunk exhausted: this lane waits for its warp-mates at the next barrier
-                }
-                if (!have) continue; // resolved without walking (index hit / dangling start): fetch again
-            }
-            // one Philox block = two steps; counter = (walk index lo, hi, block, source)
-            const Philox4 rnd = philox4x32_10(jlo, jhi, blk++, (u32)start, k0, k1);
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const u32 r_stop = half ? rnd.z : rnd.x;
-                const u32 r_pick = half ? rnd.w : rnd.y;
-                if (!first && r_stop < a.alpha_thr) { // algo.h:131-133
-                    atomicAdd(&ppr[cur], inc);
-                    have = false;
-                    break;
-                }
-                first = false;
-                const OffT b = g.ptr[cur];
-                const u32 d = (u32)(g.ptr[cur + 1] - b);
-                if (d) {
-                    const OffT pos = b + (OffT)__umulhi(r_pick, d); // algo.h:135-136
-                    if (!HINT || ((u64)pos < a.hot_elems && !a.hot_keep)) cur = __ldg(&g.col[pos]);
-                    else cur = ld_s32_hint(&g.col[pos], (u64)pos < a.hot_elems ? pol_keep : pol_stream);
-                    ++my_hops;
-                } else {
-                    cur = start; // algo.h:138-140
-                }
-            }
-        }
-    }
-    my_hops = warp_sum(my_hops);
-    my_hits = warp_sum(my_hits);
-    if (lane_id() == 0) {
-        if (my_hops) atomicAdd(&a.hops[slot], my_hops);
-        if (my_hits) atomicAdd(&a.idx_hits[slot], my_hits);
-    }
-}
-
-// Warp-converged variant of the same loop (identical Philox counters, hence identical destinations).  In walk_kernel a
-// lane that finishes a walk goes its own way (fetch, next Philox block) while its warp-mates are still stepping and the
-// warp never meets again: measured 13.7 of 32 lanes active per issued instruction.  Here every iteration starts at an
-// explicit reconvergence point, the lanes without a walk refill together, and then ALL lanes evaluate one Philox block
-// and up to two steps together; a lane leaves the loop only when the whole warp has nothing left in this chunk.
-template <typename OffT, bool NO_ZERO_HOP, bool HINT>
-__global__ void __launch_bounds__(WALK_THREADS) walk_kernel2(WalkArgs a, CsrView<OffT> g) {
-    __shared__ long long s_rel[WALK_CHUNK + 2];
+    // walk offsets of the sources touching the chunk, relative to the chunk start.  Entries 1.. lie in (0, chunk] and fit
+    // 16 bits; entry 0 (<= 0, a source that started in an earlier chunk, possibly billions of walks ago) keeps 64 bits.
+    // 4 bytes of shared memory per walk: the chunk can be large (few chunk tails) without eating the L1.
+    static_assert(WALK_CHUNK + 1 <= 65535, "chunk offsets are staged as 16-bit values");
+    __shared__ unsigned short s_rel[WALK_CHUNK + 2];
+    __shared__ long long s_rel0;
     __shared__ unsigned short s_own[WALK_CHUNK];
     __shared__ u32 s_next;
     const int slot = a.slot0 + (int)blockIdx.y;
@@ -396,14 +284,18 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel2(WalkArgs a, CsrView
         const u32 s_lo = cfirst[chunk], s_hi = cfirst[chunk + 1];
         const u32 cnt = s_hi - s_lo + 1; // sources touching this chunk, <= WALK_CHUNK + 1
         __syncthreads();
-        for (u32 i = threadIdx.x; i <= cnt; i += WALK_THREADS) s_rel[i] = (long long)woff[s_lo + i] - (long long)w0;
+        for (u32 i = threadIdx.x; i <= cnt; i += WALK_THREADS) {
+            const long long rel = (long long)woff[s_lo + i] - (long long)w0;
+            s_rel[i] = (unsigned short)max(0ll, min(rel, (long long)WALK_CHUNK + 1)); // entry 0 and the sentinel are never compared
+            if (i == 0) s_rel0 = rel;
+        }
         if (threadIdx.x == 0) s_next = 0;
         __syncthreads();
         for (u32 x = threadIdx.x; x < nw; x += WALK_THREADS) { // expansion: owner of walk x = last i with s_rel[i] <= x
             u32 lo = 0, hi = cnt;
             while (hi - lo > 1) {
-                const u32 mid = (lo + hi) >> 1;
-                if (s_rel[mid] <= (long long)x) lo = mid;
+                const u32 mid = (lo + hi) >> 1; // >= 1
+                if ((u32)s_rel[mid] <= x) lo = mid;
                 else hi = mid;
             }
             s_own[x] = (unsigned short)lo;
@@ -423,7 +315,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel2(WalkArgs a, CsrView
                     break;
                 }
                 const u32 own = s_own[x];
-                const u64 j = (u64)((long long)x - s_rel[own]);
+                const u64 j = own ? (u64)(x - (u32)s_rel[own]) : (u64)((long long)x - s_rel0);
                 const int32_t v = srcs[s_lo + own];
                 inc = incs[s_lo + own];
                 bool done = false;
