@@ -635,7 +635,9 @@ static int pack_columns(fora_ctx* ctx) {
     if ((getenv("FORA_PUSH_PACK") && atoi(getenv("FORA_PUSH_PACK")) == 0) || g.n_edges == 0) return FORA_OK; // on by default (+6 % push edges/s)
     u32 bits = 1;
     while ((1ull << bits) < (unsigned long long)g.n) ++bits;
-    if (32 - bits < 4) return FORA_OK; // fewer than 4 spare bits: most degrees would saturate
+    // test hook: FORA_PACK_SHIFT forces more id bits (fewer degree bits), so that small graphs exercise the saturated path
+    if (getenv("FORA_PACK_SHIFT")) bits = std::max(bits, std::min(31u, (u32)atoi(getenv("FORA_PACK_SHIFT"))));
+    else if (32 - bits < 4) return FORA_OK; // fewer than 4 spare bits: most degrees would saturate
     CK(cudaMalloc((void**)&g.out_colx, sizeof(int32_t) * (size_t)g.n_edges));
     pack_columns_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(g.n_edges, g.out_col, g.deg, bits, g.out_colx);
     CKL();

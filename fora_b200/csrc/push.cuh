@@ -601,15 +601,24 @@ __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n,
     const double rm = next_rmax ? next_rmax[slot] : 0.0;
     double s = 0.0;
     u32 c = 0, ns = 0;
-    for (int v = lo + threadIdx.x; v < hi; v += RED_THREADS) {
-        const double r = res[v];
+    auto take = [&](double r, int v) { // same per-thread order as a plain strided loop: rsum stays bit-identical
         s += r;
         c += r > 0.0;
         if (rm > 0.0 && r > 0.0) {
             const int32_t d = deg[v];
             ns += d ? (r >= rm * (double)d) : 1u;
         }
+    };
+    int v = lo + threadIdx.x;
+    for (; v + 3 * RED_THREADS < hi; v += 4 * RED_THREADS) { // four independent loads in flight per thread
+        const double r0 = res[v], r1 = res[v + RED_THREADS], r2 = res[v + 2 * RED_THREADS],
+                     r3 = res[v + 3 * RED_THREADS];
+        take(r0, v);
+        take(r1, v + RED_THREADS);
+        take(r2, v + 2 * RED_THREADS);
+        take(r3, v + 3 * RED_THREADS);
     }
+    for (; v < hi; v += RED_THREADS) take(res[v], v);
     s_sum[threadIdx.x] = s;
     s_nnz[threadIdx.x] = c;
     s_seed[threadIdx.x] = ns;

@@ -97,3 +97,40 @@ def test_max_slots_and_ragged_last_wave():
     with pytest.raises(fb.ForaError):
         E.query_batch("fora", srcs)  # no graph / params
     E.close()
+
+
+@pytest.mark.parametrize("env", [
+    {"FORA_PUSH_PACK": "0"},                        # plain columns, degree loaded per edge
+    {"FORA_PACK_SHIFT": "29"},                      # 3 degree bits: every target with d_out >= 7 takes the saturated path
+    {"FORA_PACK_SHIFT": "31"},                      # 1 degree bit: only d_out = 0 is ever packed
+    {"FORA_RELABEL_KEY": "0"},                      # relabelling by plain in-degree
+    {"FORA_NO_RELABEL": "1"},                       # no relabelling at all
+    {"FORA_WALK_HOT_MB": "0.01"},                   # evict_first instantiation of the walk kernel on a small graph
+    {"FORA_WALK_HOT_MB": "0"},                      # unhinted instantiation
+])
+def test_layout_variants_give_the_same_answers(env, monkeypatch):
+    """Packed columns, relabelling keys and L2 hints are layout choices: push results must match the schedule-matched
+    oracle under each of them, walk counts must not move, and a query must still meet FORA's guarantee."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = Graph.synth(6000, 90000, seed=11)
+    E = fb.Engine(0, seed=5, slots=3)
+    E.upload_graph(g.n, g.m_decl, g.out_ptr, g.out_col)
+    op, oc, _, _ = E.download_csr(with_in=False)
+    assert (op == g.out_ptr).all() and (oc == g.out_col).all()
+    rmax, omega = E.configure("fora", 0.5, opt=1, balanced=0)
+    O = Oracle(g)
+    O.init_state(-1.0, 0)
+    hub = int(np.argmax(g.deg))
+    for s in (hub, 17):
+        res, rsd, rsum, st = E.push_only(s, rmax)
+        r2 = O.push_sync(s, rmax, 1, 0)
+        a, b = O.fwd()
+        assert relerr(res, a) < 1e-9 and relerr(rsd, b) < 1e-9 and abs(rsum - r2) < 1e-12
+    ppr, st, _ = E.query_batch("fora", np.array([hub, 17, 4000], np.int32))
+    for i, s in enumerate((hub, 17, 4000)):
+        exact = O.power_iteration(int(s), 150)
+        big = exact >= 1.0 / g.n
+        assert abs(ppr[i].sum() - 1.0) < 1e-9
+        assert (np.abs(ppr[i][big] - exact[big]) / exact[big]).max() < 0.5
+    E.close()
