@@ -756,7 +756,7 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         ctx->red_blocks = std::max(1, std::min<int>(ctx->num_sms * 4, (int)((n + 4095) / 4096)));
         CK(ctx->part_sum.ensure((size_t)ctx->red_blocks * S));
         CK(ctx->part_nnz.ensure((size_t)ctx->red_blocks * S));
-        const size_t nblk = (n + PLAN_THREADS - 1) / PLAN_THREADS;
+        const size_t nblk = (n + PLAN_THREADS * PLAN_VPT - 1) / (PLAN_THREADS * PLAN_VPT);
         CK(ctx->blk_src.ensure(nblk * S));
         CK(ctx->blk_walk.ensure(nblk * S));
         CK(ctx->srcs.ensure(n * S));
@@ -1049,7 +1049,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     pa.residue = ctx->residue.p; pa.ppr = ppr; pa.rsum = m->rsum; pa.slot_state = m->state;
     pa.blk_src = ctx->blk_src.p; pa.blk_walk = ctx->blk_walk.p; pa.srcs = ctx->srcs.p; pa.woff = ctx->woff.p;
     pa.incs = ctx->incs.p; pa.nsrc = m->nsrc; pa.nwalk = m->nwalk;
-    pa.nblk = (g.n + PLAN_THREADS - 1) / PLAN_THREADS;
+    pa.nblk = (g.n + PLAN_THREADS * PLAN_VPT - 1) / (PLAN_THREADS * PLAN_VPT);
     pa.no_credit = part > 0;
     plan_kernel<false><<<dim3(pa.nblk, S), PLAN_THREADS, 0, ctx->stream>>>(pa);
     CKL();

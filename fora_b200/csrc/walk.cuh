@@ -19,6 +19,7 @@
 namespace fora {
 
 constexpr int PLAN_THREADS = 1024;
+constexpr int PLAN_VPT = 4; // vertices per thread in the plan passes
 constexpr int WALK_THREADS = 256;
 #ifndef CFG_WALK_CHUNK
 #define CFG_WALK_CHUNK 3840
@@ -71,35 +72,44 @@ __device__ __forceinline__ void plan_one(const PlanArgs& a, double r, double che
     *inc = __ddiv_rn(__dmul_rn(a_s, check_rsum), (double)num_random_walk);
 }
 
-// pass 1 (count) and pass 2 (fill) share the per-vertex evaluation; FILL selects the pass.
+// pass 1 (count) and pass 2 (fill) share the per-vertex evaluation; FILL selects the pass.  Every thread owns
+// PLAN_VPT consecutive vertices (all their loads in flight together; one vertex per thread left the pass bound by
+// block turnover: 151 K blocks of one load + two barriers each), so compaction keeps ascending vertex order.
 template <bool FILL>
 __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(PlanArgs a) {
     __shared__ u32 s_wsrc[PLAN_THREADS / WARP];
     __shared__ u64 s_wwalk[PLAN_THREADS / WARP];
     const int slot = blockIdx.y;
     if (a.slot_state[slot] == 0) return;
-    const int v = blockIdx.x * PLAN_THREADS + threadIdx.x;
-    const size_t gi = (size_t)slot * a.n + (v < a.n ? v : 0);
+    const int v0 = (blockIdx.x * PLAN_THREADS + threadIdx.x) * PLAN_VPT;
+    const size_t g0 = (size_t)slot * a.n;
     double check_rsum = a.rsum[slot];
     if (a.opt) check_rsum = __dmul_rn(check_rsum, 1.0 - a.alpha);
     const u64 num_random_walk = (u64)__dmul_rn(a.omega, check_rsum);
+    const bool live = a.slot_state[slot] == 1;
 
-    double r = 0.0;
-    u64 n_v = 0;
-    double inc = 0.0;
-    if (v < a.n && a.slot_state[slot] == 1) {
-        r = a.residue[gi];
-        if (r > 0.0) {
-            double rw = r;
-            if (a.opt) rw = __dmul_rn(r, 1.0 - a.alpha);
-            plan_one(a, rw, check_rsum, num_random_walk, &n_v, &inc);
+    double r[PLAN_VPT], inc[PLAN_VPT];
+    u64 n_v[PLAN_VPT];
+#pragma unroll
+    for (int k = 0; k < PLAN_VPT; ++k) r[k] = (live && v0 + k < a.n) ? a.residue[g0 + v0 + k] : 0.0;
+    u32 flags = 0;
+    u64 walks = 0;
+#pragma unroll
+    for (int k = 0; k < PLAN_VPT; ++k) {
+        n_v[k] = 0;
+        inc[k] = 0.0;
+        if (r[k] > 0.0) {
+            double rw = r[k];
+            if (a.opt) rw = __dmul_rn(r[k], 1.0 - a.alpha);
+            plan_one(a, rw, check_rsum, num_random_walk, &n_v[k], &inc[k]);
+            ++flags;
+            walks += n_v[k];
         }
     }
-    const u32 flag = r > 0.0;
-    // block-wide exclusive scan of (flag, n_v): warp scan + scan of warp totals
+    // block-wide exclusive scan of (sources, walks) per thread: warp scan + scan of warp totals
     const int lane = lane_id(), w = threadIdx.x >> 5;
-    const u32 fs = warp_incl_scan(flag);
-    const u64 ws = warp_incl_scan64(n_v);
+    const u32 fs = warp_incl_scan(flags);
+    const u64 ws = warp_incl_scan64(walks);
     if (lane == 31) {
         s_wsrc[w] = fs;
         s_wwalk[w] = ws;
@@ -119,13 +129,20 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(PlanArgs a) {
     }
     if (!FILL) return;
     __syncthreads();
-    if (v < a.n && flag) {
-        const size_t pos = (size_t)a.blk_src[(size_t)slot * a.nblk + blockIdx.x] + s_wsrc[w] + (fs - flag);
-        const u64 wo = a.blk_walk[(size_t)slot * a.nblk + blockIdx.x] + s_wwalk[w] + (ws - n_v);
-        a.srcs[(size_t)slot * a.n + pos] = v;
-        a.woff[(size_t)slot * (a.n + 1) + pos] = wo;
-        a.incs[(size_t)slot * a.n + pos] = inc;
-        if ((a.opt || a.per_round == 2) && !a.no_credit) a.ppr[gi] += __dmul_rn(r, a.alpha); // query.h:363 / 562
+    if (flags) {
+        size_t pos = (size_t)a.blk_src[(size_t)slot * a.nblk + blockIdx.x] + s_wsrc[w] + (fs - flags);
+        u64 wo = a.blk_walk[(size_t)slot * a.nblk + blockIdx.x] + s_wwalk[w] + (ws - walks);
+        const bool credit = (a.opt || a.per_round == 2) && !a.no_credit;
+#pragma unroll
+        for (int k = 0; k < PLAN_VPT; ++k) {
+            if (!(r[k] > 0.0)) continue;
+            a.srcs[g0 + pos] = v0 + k;
+            a.woff[(size_t)slot * (a.n + 1) + pos] = wo;
+            a.incs[g0 + pos] = inc[k];
+            if (credit) a.ppr[g0 + v0 + k] += __dmul_rn(r[k], a.alpha); // query.h:363 / 562
+            ++pos;
+            wo += n_v[k];
+        }
     }
 }
 
