@@ -777,7 +777,7 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         ctx->push_grid = std::min(per_sm * ctx->num_sms, MAX_PUSH_CTAS);
     }
     // walks per slot <= omega*rsum + #sources <= omega + n
-    const size_t need = (size_t)((omega_max + (double)n) / WALK_CHUNK) + 4;
+    const size_t need = std::max((size_t)WALK_TARGET_CHUNKS + 1, (size_t)((omega_max + (double)n) / WALK_CHUNK)) + 4; // see walk_chunk_size
     if (need > ctx->chunk_cap || ctx->chunk_first.cap < need * S) {
         CK(ctx->chunk_first.ensure(need * S));
         ctx->chunk_cap = need;

@@ -28,6 +28,14 @@ constexpr int WALK_THREADS = 256;
 // carve-out (124 KB of L1 left).  Larger chunks = fewer chunk tails (lanes idle while the longest walks of a chunk
 // finish): 1024: 98.6, 2048: 108.6, 2560: 110.9, 3840: 113.6, 4608 (next carve-out step): 102.3 G hops/s.
 constexpr int WALK_CHUNK = CFG_WALK_CHUNK;
+// A slot with few walks (a top-k round, a small graph) uses smaller chunks so that its walks still spread over the whole
+// grid: chunk = walks / WALK_TARGET_CHUNKS rounded up to 256, within [256, WALK_CHUNK].  Evaluated identically by
+// chunk_start_kernel and walk_kernel (and on every GPU of a split query) from the slot's walk count.
+constexpr int WALK_TARGET_CHUNKS = 148 * 8 * 4;
+__host__ __device__ __forceinline__ u32 walk_chunk_size(u64 walks) {
+    const u64 c = ((walks / WALK_TARGET_CHUNKS) + 255) & ~255ull;
+    return (u32)(c < 256 ? 256 : (c > (u64)WALK_CHUNK ? (u64)WALK_CHUNK : c));
+}
 
 struct PlanArgs {
     int32_t n;
@@ -196,7 +204,7 @@ __global__ void __launch_bounds__(1024) plan_scan_kernel(PlanArgs a) {
     }
 }
 
-// chunk c of slot s starts inside source chunk_first[c]: largest i with woff[i] <= c*WALK_CHUNK.
+// chunk c of slot s starts inside source chunk_first[c]: largest i with woff[i] <= c * chunk size of the slot.
 __global__ void __launch_bounds__(256) chunk_start_kernel(int32_t n, const u64* __restrict__ woff,
                                                           const u64* __restrict__ nsrc, const u64* __restrict__ nwalk,
                                                           u32* __restrict__ chunk_first, size_t chunk_cap,
@@ -204,11 +212,12 @@ __global__ void __launch_bounds__(256) chunk_start_kernel(int32_t n, const u64* 
     const int slot = blockIdx.y;
     if (slot_state[slot] != 1) return;
     const u64 W = nwalk[slot];
-    const u64 nchunks = (W + WALK_CHUNK - 1) / WALK_CHUNK;
+    const u64 CH = walk_chunk_size(W);
+    const u64 nchunks = (W + CH - 1) / CH;
     const u64* __restrict__ wo = woff + (size_t)slot * (n + 1);
     const u64 ns = nsrc[slot];
     for (u64 c = blockIdx.x * (u64)blockDim.x + threadIdx.x; c <= nchunks && c < chunk_cap; c += (u64)gridDim.x * blockDim.x) {
-        const u64 target = c * WALK_CHUNK;
+        const u64 target = c * CH;
         u64 lo = 0, hi = ns; // invariant: wo[lo] <= target; answer in [lo, hi)
         if (c == nchunks) {
             chunk_first[(size_t)slot * chunk_cap + c] = (u32)(ns ? ns - 1 : 0);
@@ -282,7 +291,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
     if (a.slot_state[slot] != 1) return;
     const u64 W = a.nwalk[slot];
     if (W == 0) return;
-    const u64 nchunks = (W + WALK_CHUNK - 1) / WALK_CHUNK;
+    const u32 CH = walk_chunk_size(W);
+    const u64 nchunks = (W + CH - 1) / CH;
     const int32_t* __restrict__ srcs = a.srcs + (size_t)slot * a.n;
     const u64* __restrict__ woff = a.woff + (size_t)slot * (a.n + 1);
     const double* __restrict__ incs = a.incs + (size_t)slot * a.n;
@@ -296,10 +306,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
     const u64 chunk_lo = a.nparts > 1 ? nchunks * a.part / a.nparts : 0;
     const u64 chunk_hi = a.nparts > 1 ? nchunks * (a.part + 1) / a.nparts : nchunks;
     for (u64 chunk = chunk_lo + blockIdx.x; chunk < chunk_hi; chunk += gridDim.x) {
-        const u64 w0 = chunk * WALK_CHUNK;
-        const u32 nw = (u32)(min(W, w0 + (u64)WALK_CHUNK) - w0);
+        const u64 w0 = chunk * CH;
+        const u32 nw = (u32)(min(W, w0 + (u64)CH) - w0);
         const u32 s_lo = cfirst[chunk], s_hi = cfirst[chunk + 1];
-        const u32 cnt = s_hi - s_lo + 1; // sources touching this chunk, <= WALK_CHUNK + 1
+        const u32 cnt = s_hi - s_lo + 1; // sources touching this chunk, <= CH + 1
         __syncthreads();
         for (u32 i = threadIdx.x; i <= cnt; i += WALK_THREADS) {
             const long long rel = (long long)woff[s_lo + i] - (long long)w0;
