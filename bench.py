@@ -212,8 +212,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="lj", choices=sorted(SHAPES))
     ap.add_argument("--batch", type=int, default=192, help="queries per step per GPU")
-    ap.add_argument("--slots", type=int, default=int(os.environ.get("FORA_SLOTS", "32")))
-    ap.add_argument("--e2e-queries", type=int, default=128)
+    ap.add_argument("--slots", type=int, default=int(os.environ.get("FORA_SLOTS", "48")))
+    ap.add_argument("--e2e-queries", type=int, default=144)
     ap.add_argument("--cpu-sample", type=int, default=1, help="queries timed on the CPU baseline (0 = skip)")
     ap.add_argument("--ref-procs", type=int, default=0, help="worker processes of the reference arm (0 = one per host core)")
     ap.add_argument("--ref-queries-per-proc", type=int, default=1)
