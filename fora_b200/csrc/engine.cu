@@ -119,6 +119,13 @@ struct fora_ctx {
     DevBuf<double> ub, lb;   // non --opt top-k: per-node upper / lower PPR bounds (algo.h:48-49)
     DevBuf<unsigned char> in_topk;
     DevBuf<u32> flags;
+    // batched select (topk.cuh): per-vector state, candidate lists, output lists
+    DevBuf<SelSlot> sel_st;
+    DevBuf<SelResult> sel_res;
+    DevBuf<int32_t> sel_slots, sel_ci, sel_on;
+    DevBuf<u64> sel_ck;
+    DevBuf<double> sel_ov;
+    u32 sel_p2 = 0;
     DevBuf<u64> idx_used;    // top-k with index: per-(slot,vertex) cursor into the index (rw_counter, query.h:575-603)
     size_t chunk_cap = 0;
     // index
@@ -259,6 +266,7 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
     ctx->ppr.release(); ctx->ub.release(); ctx->lb.release(); ctx->in_topk.release(); ctx->flags.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
+    ctx->sel_st.release(); ctx->sel_res.release(); ctx->sel_slots.release(); ctx->sel_ci.release(); ctx->sel_on.release(); ctx->sel_ck.release(); ctx->sel_ov.release();
     ctx->counts.release(); ctx->bwd_res.release(); ctx->bwd_rv.release(); ctx->bwd_lists.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
     if (ctx->h_meta) cudaFreeHost(ctx->h_meta);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -1110,6 +1118,47 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     return FORA_OK;
 }
 
+// Top-k select of `nsl` dense vectors base + stride*slots[j] in four launches (topk.cuh).  Afterwards the (optionally sorted)
+// output list of vector j is ctx->sel_on.p / sel_ov.p + j*ctx->sel_p2, h_res[j] holds its k-th key and entry count.
+static int select_batch(fora_ctx* ctx, const double* base, size_t stride, const int* slots, int nsl, u32 k, bool sort, SelResult* h_res) {
+    if (nsl <= 0) return FORA_OK;
+    if (nsl > MAX_SLOTS) return ctx->fail(FORA_EINVAL, "select_batch: too many vectors");
+    const int32_t n = ctx->g.n;
+    u32 p2 = 1;
+    while (p2 < k) p2 <<= 1;
+    CK(ctx->sel_st.ensure(MAX_SLOTS));
+    CK(ctx->sel_res.ensure(MAX_SLOTS));
+    CK(ctx->sel_slots.ensure(MAX_SLOTS));
+    CK(ctx->sel_on.ensure((size_t)p2 * MAX_SLOTS));
+    CK(ctx->sel_ov.ensure((size_t)p2 * MAX_SLOTS));
+    ctx->sel_p2 = p2;
+    const size_t cand = (size_t)n * (size_t)std::max(nsl, ctx->slots); // worst case: every entry shares the k-th entry's exponent
+    CK(ctx->sel_ck.ensure(cand));
+    CK(ctx->sel_ci.ensure(cand));
+    int32_t ids[MAX_SLOTS];
+    for (int j = 0; j < nsl; ++j) ids[j] = slots[j];
+    CK(cudaMemcpyAsync(ctx->sel_slots.p, ids, sizeof(int32_t) * nsl, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->sel_st.p, 0, sizeof(SelSlot) * nsl, ctx->stream));
+    const int gx = std::max(1, std::min(std::max(ctx->num_sms * 16 / nsl, 8), (n + 255) / 256));
+    sel_hist_kernel<<<dim3(gx, nsl), 256, 0, ctx->stream>>>(base, stride, n, ctx->sel_slots.p, ctx->sel_st.p);
+    CKL();
+    sel_pick_kernel<<<nsl, 256, 0, ctx->stream>>>(ctx->sel_st.p, k);
+    CKL();
+    sel_classify_kernel<<<dim3(gx, nsl), 256, 0, ctx->stream>>>(base, stride, n, ctx->sel_slots.p, ctx->sel_st.p, ctx->sel_ck.p, ctx->sel_ci.p, (size_t)n,
+                                                               ctx->sel_on.p, ctx->sel_ov.p, p2);
+    CKL();
+    sel_finish_kernel<<<nsl, 1024, 0, ctx->stream>>>(ctx->sel_st.p, ctx->sel_res.p, ctx->sel_ck.p, ctx->sel_ci.p, (size_t)n, ctx->sel_on.p, ctx->sel_ov.p, p2, k, sort ? 1 : 0);
+    CKL();
+    CK(cudaMemcpyAsync(h_res, ctx->sel_res.p, sizeof(SelResult) * nsl, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return FORA_OK;
+}
+static inline double sel_kth(const SelResult& r) { // kth_ppr(): 0 when there are fewer than k positive entries
+    double t = 0.0;
+    if (!r.all_positive) memcpy(&t, &r.key_T, sizeof t);
+    return t;
+}
+
 static void fill_stat(fora_ctx* ctx, int s, double final_rmax, u64 rounds, fora_query_stat* st) {
     const SlotMeta* h = ctx->h_meta;
     memset(st, 0, sizeof *st);
@@ -1682,6 +1731,7 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
                 }
                 if ((rc = meta_d2h_sync(ctx))) return restore(rc);
                 CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+                std::vector<int> act, need_lb;
                 for (int s = 0; s < cnt; ++s) {
                     if (done[s]) continue;
                     tot_walks[s] += h->nwalk[s]; tot_hits[s] += h->idx_hits[s]; tot_hops[s] += h->hops[s];
@@ -1692,34 +1742,39 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
                                                                                    ctx->ub.p + nn * s, ctx->lb.p + nn * s);
                         CKL();
                     }
-                    // if_stop(), algo.h:1096-1166
-                    bool stop = false;
-                    double kth = 0.0;
-                    cudaError_t e = topk_device(ctx->stream, ctx->num_sms, ctx->ppr.p + nn * s, n, k, nullptr, nullptr, &ctx->launches, &kth);
-                    if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("kth select: ") + cudaGetErrorString(e)));
-                    if (kth >= 2.0 * delta) stop = true;
-                    else if (!(delta >= threshold)) {
-                        int32_t* d_nodes = nullptr;
-                        u32 got = 0;
-                        double low_k = 0.0;
-                        e = topk_device(ctx->stream, ctx->num_sms, ctx->lb.p + nn * s, n, k, nullptr, nullptr, &ctx->launches, &low_k, &d_nodes, &got);
-                        if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("bound select: ") + cudaGetErrorString(e)));
-                        // fewer than k positive lower bounds: some top-k node has lower bound 0 => ratio test fails (algo.h:1129-1134)
-                        if (got == k && low_k > delta) {
-                            CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(u32) * 4, ctx->stream));
-                            stop_mark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->ub.p + nn * s, ctx->lb.p + nn * s, keep.epsilon, ctx->in_topk.p, ctx->flags.p);
-                            stop_tail_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, ctx->ppr.p + nn * s, ctx->ub.p + nn * s, ctx->lb.p + nn * s, ctx->in_topk.p, low_k,
-                                                                                      keep.epsilon, ctx->flags.p);
-                            stop_unmark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->in_topk.p);
-                            ctx->launches += 3;
-                            u32 hf[2];
-                            CK(cudaMemcpyAsync(hf, ctx->flags.p, sizeof(u32) * 2, cudaMemcpyDeviceToHost, ctx->stream));
-                            CK(cudaStreamSynchronize(ctx->stream));
-                            stop = !hf[0] && !hf[1];
-                        }
-                    }
-                    if (stop || delta <= min_delta) done[s] = 1; // query.h:963
+                    act.push_back(s);
                 }
+                // if_stop(), algo.h:1096-1166: k-th estimate of every active slot in one batched select ...
+                std::vector<SelResult> sres(MAX_SLOTS);
+                std::vector<char> stop(cnt, 0);
+                if ((rc = select_batch(ctx, ctx->ppr.p, nn, act.data(), (int)act.size(), k, false, sres.data()))) return restore(rc);
+                for (size_t j = 0; j < act.size(); ++j) {
+                    if (sel_kth(sres[j]) >= 2.0 * delta) stop[act[j]] = 1;
+                    else if (!(delta >= threshold)) need_lb.push_back(act[j]);
+                }
+                // ... then the k largest lower bounds of the slots that are still open
+                if ((rc = select_batch(ctx, ctx->lb.p, nn, need_lb.data(), (int)need_lb.size(), k, false, sres.data()))) return restore(rc);
+                for (size_t j = 0; j < need_lb.size(); ++j) {
+                    const int s = need_lb[j];
+                    const int32_t* d_nodes = ctx->sel_on.p + (size_t)ctx->sel_p2 * j;
+                    const u32 got = sres[j].out_count;
+                    const double low_k = sel_kth(sres[j]);
+                    // fewer than k positive lower bounds: some top-k node has lower bound 0 => ratio test fails (algo.h:1129-1134)
+                    if (got == k && low_k > delta) {
+                        CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(u32) * 4, ctx->stream));
+                        stop_mark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->ub.p + nn * s, ctx->lb.p + nn * s, keep.epsilon, ctx->in_topk.p, ctx->flags.p);
+                        stop_tail_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, ctx->ppr.p + nn * s, ctx->ub.p + nn * s, ctx->lb.p + nn * s, ctx->in_topk.p, low_k,
+                                                                                  keep.epsilon, ctx->flags.p);
+                        stop_unmark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->in_topk.p);
+                        ctx->launches += 3;
+                        u32 hf[2];
+                        CK(cudaMemcpyAsync(hf, ctx->flags.p, sizeof(u32) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+                        CK(cudaStreamSynchronize(ctx->stream));
+                        stop[s] = !hf[0] && !hf[1];
+                    }
+                }
+                for (int s : act)
+                    if (stop[s] || delta <= min_delta) done[s] = 1; // query.h:963
                 CK(cudaEventRecord(ctx->ev[7], ctx->stream));
                 CK(cudaEventSynchronize(ctx->ev[7]));
                 float t;
@@ -1777,14 +1832,16 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
                 }
                 if ((rc = meta_d2h_sync(ctx))) return restore(rc);
                 CK(cudaEventRecord(ctx->ev[6], ctx->stream));
+                std::vector<int> act;
                 for (int s = 0; s < cnt; ++s) {
                     if (done[s]) continue;
                     tot_walks[s] += h->nwalk[s]; tot_hits[s] += h->idx_hits[s]; tot_hops[s] += h->hops[s];
-                    double kth = 0.0; // kth_ppr(), algo.h:578-590
-                    cudaError_t e = topk_device(ctx->stream, ctx->num_sms, ctx->ppr.p + nn * s, n, k, nullptr, nullptr, &ctx->launches, &kth);
-                    if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("kth select: ") + cudaGetErrorString(e)));
-                    if (kth >= (1 + keep.epsilon) * delta || delta <= min_delta) done[s] = 1; // query.h:1029
+                    act.push_back(s);
                 }
+                std::vector<SelResult> sres(MAX_SLOTS);
+                if ((rc = select_batch(ctx, ctx->ppr.p, nn, act.data(), (int)act.size(), k, false, sres.data()))) return restore(rc); // kth_ppr(), algo.h:578-590
+                for (size_t j = 0; j < act.size(); ++j)
+                    if (sel_kth(sres[j]) >= (1 + keep.epsilon) * delta || delta <= min_delta) done[act[j]] = 1; // query.h:1029
                 CK(cudaEventRecord(ctx->ev[7], ctx->stream));
                 CK(cudaEventSynchronize(ctx->ev[7]));
                 float t;
@@ -1807,14 +1864,25 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
             if (stats) for (int s = 0; s < cnt; ++s) stats[q0 + s] = st[s];
         }
         CK(cudaEventRecord(ctx->ev[6], ctx->stream));
-        for (int s = 0; s < cnt; ++s) { // topk_ppr(), algo.h:592-610
-            cudaError_t e = topk_device(ctx->stream, ctx->num_sms, result + nn * s, n, k, nodes + (size_t)(q0 + s) * k, values + (size_t)(q0 + s) * k, &ctx->launches);
-            if (e != cudaSuccess) return restore(ctx->fail(FORA_ECUDA, std::string("topk: ") + cudaGetErrorString(e)));
-            if (ctx->g.relabeled) { // internal -> original ids; unfilled slots stay (0, 0.0)
+        { // topk_ppr(), algo.h:592-610: all slots of the wave in one batched select, sorted on the device
+            std::vector<int> all(cnt);
+            for (int s = 0; s < cnt; ++s) all[s] = s;
+            std::vector<SelResult> sres(MAX_SLOTS);
+            if ((rc = select_batch(ctx, result, nn, all.data(), cnt, k, true, sres.data()))) return restore(rc);
+            for (int s = 0; s < cnt; ++s) {
+                const u32 got = sres[s].out_count;
+                if (got) {
+                    CK(cudaMemcpyAsync(nodes + (size_t)(q0 + s) * k, ctx->sel_on.p + (size_t)ctx->sel_p2 * s, sizeof(int32_t) * got, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaMemcpyAsync(values + (size_t)(q0 + s) * k, ctx->sel_ov.p + (size_t)ctx->sel_p2 * s, sizeof(double) * got, cudaMemcpyDeviceToHost, ctx->stream));
+                }
+            }
+            CK(cudaStreamSynchronize(ctx->stream));
+            for (int s = 0; s < cnt; ++s) {
                 int32_t* nd = nodes + (size_t)(q0 + s) * k;
-                const double* vl = values + (size_t)(q0 + s) * k;
-                for (uint32_t j = 0; j < k; ++j)
-                    if (vl[j] > 0.0) nd[j] = to_original(ctx, nd[j]);
+                double* vl = values + (size_t)(q0 + s) * k;
+                for (uint32_t j = sres[s].out_count; j < k; ++j) { nd[j] = 0; vl[j] = 0.0; } // unfilled slots stay (0, 0.0)
+                if (ctx->g.relabeled) // internal -> original ids
+                    for (uint32_t j = 0; j < sres[s].out_count; ++j) nd[j] = to_original(ctx, nd[j]);
             }
         }
         CK(cudaEventRecord(ctx->ev[7], ctx->stream));
@@ -1953,10 +2021,16 @@ extern "C" int fora_topk_of(fora_ctx* ctx, const double* ppr, uint32_t k, int32_
     const size_t n = (size_t)ctx->g.n;
     CK(ctx->scratchd.ensure(n));
     CK(cudaMemcpyAsync(ctx->scratchd.p, ppr, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    TopkWork tw;
-    cudaError_t e = topk_device(ctx->stream, ctx->num_sms, ctx->scratchd.p, ctx->g.n, k, nodes, values, &ctx->launches);
-    if (e != cudaSuccess) return ctx->fail(FORA_ECUDA, std::string("topk: ") + cudaGetErrorString(e));
-    (void)tw;
+    const int zero = 0;
+    SelResult r;
+    int rc = select_batch(ctx, ctx->scratchd.p, 0, &zero, 1, k, true, &r);
+    if (rc) return rc;
+    if (r.out_count) {
+        CK(cudaMemcpyAsync(nodes, ctx->sel_on.p, sizeof(int32_t) * r.out_count, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(values, ctx->sel_ov.p, sizeof(double) * r.out_count, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (uint32_t j = r.out_count; j < k; ++j) { nodes[j] = 0; values[j] = 0.0; }
     return FORA_OK;
 }
 

@@ -1,10 +1,9 @@
 // fora_b200/csrc/topk.cuh -- top-k / k-th value selection and the dense power iteration.
 //
 // Replaces kth_ppr / topk_ppr (/root/reference/algo.h:578-610: nth_element / partial_sort_copy over
-// the touched entries) with a radix select over the dense fp64 vector: positive doubles order like
-// their bit patterns, so the k-th largest value is found digit by digit (8 passes of 8 bits, one
-// 256-bin shared-memory histogram per block per pass).  Ties at the k-th value are broken towards
-// the smaller node id by continuing the select over the id bits, which makes the result unique
+// the touched entries) with a radix select over the dense fp64 vectors of a whole wave of query slots: positive
+// doubles order like their bit patterns, so the k-th largest value is found digit by digit.  Ties at the k-th value
+// are broken towards the smaller node id by continuing the select over the id bits, which makes the result unique
 // and reproducible (the reference leaves tie order unspecified).
 // Slots beyond the number of positive entries stay (0, 0.0) as in algo.h:593-594.
 //
@@ -14,137 +13,113 @@
 
 namespace fora {
 
-struct TopkWork {};
-
-struct SelectState {
-    u64 prefix;     // high bits of the key decided so far
-    u64 remaining;  // how many elements still to take inside the current prefix
-    u64 n_positive;
-    u64 key_T;      // k-th largest key (valid after the value passes)
-    u64 need_eq;    // how many elements with key == key_T belong to the top-k
-    u64 count_eq;
-    u32 id_prefix;  // tie-break select over ids (ascending)
-    u32 id_T;       // largest id taken among the ties
-    u32 hist[256];
-    u32 out_count;
-    u32 all_positive; // fewer than k positive entries: take them all
-};
-
 __device__ __forceinline__ u64 topk_key(double v) { return v > 0.0 ? (u64)__double_as_longlong(v) : 0ull; }
 
-// histogram of digit `shift` among elements whose key matches `prefix` on the bits above it
-__global__ void __launch_bounds__(256) topk_hist_kernel(const double* __restrict__ vals, int32_t n, SelectState* st, int shift) {
-    __shared__ u32 s_h[256];
-    s_h[threadIdx.x] = 0;
+// ---------------------------------------------------------------------------------------------
+// Batched select over MANY dense vectors (one per query slot): two passes over each vector and four launches for all of
+// them (the first version selected slot by slot with 12 full passes and ~27 launches per vector, which left a top-k
+// round launch- and sync-bound):
+//   1. sel_hist_kernel      2048-bin histogram of the top 12 key bits (sign + exponent) of every positive entry
+//   2. sel_pick_kernel      the bin holding the k-th largest entry, and how many entries lie above it
+//   3. sel_classify_kernel  entries above the bin go straight to the output list, entries inside it to a candidate list
+//   4. sel_finish_kernel    one CTA per vector finishes on the (small) candidate list: the remaining 52 key bits in
+//                           8-bit digits, ties at the k-th value towards the smaller id, collect, optional bitonic sort
+// ---------------------------------------------------------------------------------------------
+constexpr int SEL_BINS = 2048;
+struct SelSlot {
+    u32 hist[SEL_BINS];
+    u32 bin, above, n_positive, all_positive;
+    u32 cand_count, out_count;
+};
+struct SelResult {
+    u64 key_T;      // k-th largest key; 0 when the vector has fewer than k positive entries
+    u32 out_count;  // entries in the output list (<= k)
+    u32 all_positive;
+};
+
+__global__ void __launch_bounds__(256) sel_hist_kernel(const double* __restrict__ base, size_t stride, int32_t n,
+                                                        const int32_t* __restrict__ slot_ids, SelSlot* st) {
+    __shared__ u32 s_h[SEL_BINS];
+    for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x) s_h[b] = 0;
     __syncthreads();
-    const u64 prefix = st->prefix;
-    const u64 hi_mask = shift >= 56 ? 0ull : (~0ull << (shift + 8));
+    const double* __restrict__ vals = base + stride * (size_t)slot_ids[blockIdx.y];
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const u64 key = topk_key(vals[i]);
-        if (key != 0 && (key & hi_mask) == prefix) atomicAdd(&s_h[(key >> shift) & 0xff], 1u);
+        if (key) atomicAdd(&s_h[key >> 52], 1u);
     }
     __syncthreads();
-    if (s_h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], s_h[threadIdx.x]);
+    for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x)
+        if (s_h[b]) atomicAdd(&st[blockIdx.y].hist[b], s_h[b]);
 }
 
-// pick the digit that contains the `remaining`-th largest element, descend into it
-__global__ void topk_pick_kernel(SelectState* st, int shift, u64 k) {
-    if (threadIdx.x != 0) return;
-    if (shift == 56) { // first pass: initialise
-        u64 total = 0;
-        for (int b = 0; b < 256; ++b) total += st->hist[b];
-        st->n_positive = total;
-        st->remaining = k;
-        st->all_positive = total < k;
+__global__ void __launch_bounds__(256) sel_pick_kernel(SelSlot* st, u32 k) {
+    __shared__ u32 red[256];
+    SelSlot& s = st[blockIdx.x];
+    u32 t = 0;
+    for (int b = threadIdx.x; b < SEL_BINS; b += blockDim.x) t += s.hist[b];
+    red[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
     }
-    if (!st->all_positive) {
-        u64 rem = st->remaining;
-        for (int b = 255; b >= 0; --b) {
-            const u64 c = st->hist[b];
-            if (c >= rem) {
-                st->prefix |= (u64)b << shift;
-                if (shift == 0) { st->count_eq = c; st->need_eq = rem; st->key_T = st->prefix; }
-                break;
-            }
+    if (threadIdx.x != 0) return;
+    s.n_positive = red[0];
+    s.all_positive = red[0] < k;
+    s.bin = 0;
+    s.above = 0;
+    if (!s.all_positive) {
+        u32 rem = k;
+        for (int b = SEL_BINS - 1; b >= 0; --b) {
+            const u32 c = s.hist[b];
+            if (c >= rem) { s.bin = (u32)b; s.above = k - rem; break; }
             rem -= c;
         }
-        st->remaining = rem;
-    } else if (shift == 0) {
-        st->key_T = 1; // every positive key is > 0: take all of them
-        st->need_eq = 0;
-        st->count_eq = 0;
     }
-    for (int b = 0; b < 256; ++b) st->hist[b] = 0;
 }
 
-// tie-break: among key == key_T select the need_eq smallest ids (ascending radix select over 32 bits)
-__global__ void __launch_bounds__(256) topk_idhist_kernel(const double* __restrict__ vals, int32_t n, SelectState* st, int shift) {
-    __shared__ u32 s_h[256];
-    s_h[threadIdx.x] = 0;
-    __syncthreads();
-    if (st->all_positive || st->need_eq == st->count_eq) return;
-    const u64 T = st->key_T;
-    const u32 prefix = st->id_prefix;
-    const u32 hi_mask = shift >= 24 ? 0u : (~0u << (shift + 8));
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        if (topk_key(vals[i]) == T && ((u32)i & hi_mask) == prefix) atomicAdd(&s_h[((u32)i >> shift) & 0xff], 1u);
-    }
-    __syncthreads();
-    if (s_h[threadIdx.x]) atomicAdd(&st->hist[threadIdx.x], s_h[threadIdx.x]);
-}
-__global__ void topk_idpick_kernel(SelectState* st, int shift) {
-    if (threadIdx.x != 0) return;
-    if (st->all_positive || st->need_eq == st->count_eq) {
-        st->id_T = 0xffffffffu;
-        return;
-    }
-    if (shift == 24) st->remaining = st->need_eq;
-    u64 rem = st->remaining;
-    for (int b = 0; b < 256; ++b) {
-        const u64 c = st->hist[b];
-        if (c >= rem) {
-            st->id_prefix |= (u32)b << shift;
-            break;
-        }
-        rem -= c;
-    }
-    st->remaining = rem;
-    if (shift == 0) st->id_T = st->id_prefix;
-    for (int b = 0; b < 256; ++b) st->hist[b] = 0;
-}
-
-__global__ void __launch_bounds__(256) topk_collect_kernel(const double* __restrict__ vals, int32_t n, SelectState* st,
-                                                            int32_t* __restrict__ out_nodes, double* __restrict__ out_vals, u32 cap) {
-    const u64 T = st->key_T;
-    const u32 idT = st->id_T;
-    const bool all = st->all_positive;
+__global__ void __launch_bounds__(256) sel_classify_kernel(const double* __restrict__ base, size_t stride, int32_t n,
+                                                            const int32_t* __restrict__ slot_ids, SelSlot* st,
+                                                            u64* __restrict__ cand_keys, int32_t* __restrict__ cand_ids, size_t cand_stride,
+                                                            int32_t* __restrict__ out_nodes, double* __restrict__ out_vals, u32 out_stride) {
+    SelSlot& s = st[blockIdx.y];
+    const double* __restrict__ vals = base + stride * (size_t)slot_ids[blockIdx.y];
+    const bool all = s.all_positive;
+    const u32 bin = s.bin;
+    u64* ck = cand_keys + cand_stride * blockIdx.y;
+    int32_t* ci = cand_ids + cand_stride * blockIdx.y;
+    int32_t* on = out_nodes + (size_t)out_stride * blockIdx.y;
+    double* ov = out_vals + (size_t)out_stride * blockIdx.y;
     const int iters = (n + WARP - 1) / WARP;
     for (int wi = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; wi < iters; wi += (gridDim.x * blockDim.x) >> 5) {
         const int i = wi * WARP + lane_id();
-        bool take = false;
-        double v = 0.0;
-        if (i < n) {
-            v = vals[i];
-            const u64 key = topk_key(v);
-            take = all ? key != 0 : (key > T || (key == T && (u32)i <= idT));
+        u64 key = 0;
+        if (i < n) key = topk_key(vals[i]);
+        const u32 top = (u32)(key >> 52);
+        const bool win = key != 0 && (all || top > bin);
+        const bool cand = key != 0 && !all && top == bin;
+        const u32 mw = __ballot_sync(FULL, win), mc = __ballot_sync(FULL, cand);
+        if (mw) {
+            const int leader = __ffs(mw) - 1;
+            u32 b0 = 0;
+            if (lane_id() == leader) b0 = atomicAdd(&s.out_count, (u32)__popc(mw));
+            b0 = __shfl_sync(FULL, b0, leader);
+            const u32 pos = b0 + __popc(mw & lanemask_lt());
+            if (win && pos < out_stride) { on[pos] = i; ov[pos] = __longlong_as_double((long long)key); }
         }
-        const u32 mask = __ballot_sync(FULL, take);
-        if (mask) {
-            const int leader = __ffs(mask) - 1;
-            u32 base = 0;
-            if (lane_id() == leader) base = atomicAdd(&st->out_count, (u32)__popc(mask));
-            base = __shfl_sync(FULL, base, leader);
-            const u32 pos = base + __popc(mask & lanemask_lt());
-            if (take && pos < cap) {
-                out_nodes[pos] = i;
-                out_vals[pos] = v;
-            }
+        if (mc) {
+            const int leader = __ffs(mc) - 1;
+            u32 b0 = 0;
+            if (lane_id() == leader) b0 = atomicAdd(&s.cand_count, (u32)__popc(mc));
+            b0 = __shfl_sync(FULL, b0, leader);
+            const u32 pos = b0 + __popc(mc & lanemask_lt());
+            if (cand) { ck[pos] = key; ci[pos] = i; }
         }
     }
 }
 
-// single-block bitonic sort of `cnt` (value desc, id asc) pairs padded to a power of two `p2`
-__global__ void __launch_bounds__(1024) topk_sort_kernel(int32_t* nodes, double* vals, u32 cnt, u32 p2) {
+// bitonic sort of `cnt` (value desc, id asc) pairs padded to a power of two `p2`, by one CTA
+__device__ __forceinline__ void bitonic_sort_block(int32_t* nodes, double* vals, u32 cnt, u32 p2) {
     for (u32 i = cnt + threadIdx.x; i < p2; i += blockDim.x) { nodes[i] = 0x7fffffff; vals[i] = -1.0; }
     __syncthreads();
     for (u32 size = 2; size <= p2; size <<= 1) {
@@ -152,10 +127,10 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(int32_t* nodes, double*
             for (u32 t = threadIdx.x; t < (p2 >> 1); t += blockDim.x) {
                 const u32 lo = 2 * t - (t & (stride - 1));
                 const u32 hi = lo + stride;
-                const bool desc_block = (lo & size) == 0; // this block sorts "first" order
+                const bool desc_block = (lo & size) == 0;
                 const double a = vals[lo], b = vals[hi];
                 const int32_t ia = nodes[lo], ib = nodes[hi];
-                const bool a_first = a > b || (a == b && ia < ib); // desired order: a before b
+                const bool a_first = a > b || (a == b && ia < ib);
                 if (a_first != desc_block) {
                     vals[lo] = b; vals[hi] = a;
                     nodes[lo] = ib; nodes[hi] = ia;
@@ -166,70 +141,93 @@ __global__ void __launch_bounds__(1024) topk_sort_kernel(int32_t* nodes, double*
     }
 }
 
-// Select + sort on the device, results copied to host arrays of length k.
-static inline cudaError_t topk_device(cudaStream_t stream, int num_sms, const double* d_vals, int32_t n, u32 k,
-                                      int32_t* h_nodes, double* h_values, u64* launches, double* kth_value = nullptr,
-                                      int32_t** d_nodes_out = nullptr, u32* count_out = nullptr, bool sort_on_device = false) {
-    static thread_local SelectState* d_st = nullptr;
-    static thread_local int32_t* d_nodes = nullptr;
-    static thread_local double* d_out = nullptr;
-    static thread_local u32 d_cap = 0;
-    cudaError_t e;
-    if (!d_st && (e = cudaMalloc((void**)&d_st, sizeof(SelectState))) != cudaSuccess) return e;
-    u32 p2 = 1;
-    while (p2 < k) p2 <<= 1;
-    if (p2 > d_cap) {
-        cudaFree(d_nodes);
-        cudaFree(d_out);
-        d_nodes = nullptr; d_out = nullptr; d_cap = 0;
-        if ((e = cudaMalloc((void**)&d_nodes, sizeof(int32_t) * p2)) != cudaSuccess) return e;
-        if ((e = cudaMalloc((void**)&d_out, sizeof(double) * p2)) != cudaSuccess) return e;
-        d_cap = p2;
-    }
-    if ((e = cudaMemsetAsync(d_st, 0, sizeof(SelectState), stream)) != cudaSuccess) return e;
-    const int gx = std::max(1, std::min(num_sms * 8, (n + 255) / 256));
-    for (int shift = 56; shift >= 0; shift -= 8) {
-        topk_hist_kernel<<<gx, 256, 0, stream>>>(d_vals, n, d_st, shift);
-        topk_pick_kernel<<<1, 32, 0, stream>>>(d_st, shift, (u64)k);
-        *launches += 2;
-    }
-    for (int shift = 24; shift >= 0; shift -= 8) {
-        topk_idhist_kernel<<<gx, 256, 0, stream>>>(d_vals, n, d_st, shift);
-        topk_idpick_kernel<<<1, 32, 0, stream>>>(d_st, shift);
-        *launches += 2;
-    }
-    topk_collect_kernel<<<gx, 256, 0, stream>>>(d_vals, n, d_st, d_nodes, d_out, k);
-    *launches += 1;
-    SelectState hs;
-    if ((e = cudaMemcpyAsync(&hs, d_st, sizeof(SelectState), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-    if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-    const u32 cnt = std::min<u32>(hs.out_count, k);
-    if (d_nodes_out) *d_nodes_out = d_nodes;
-    if (count_out) *count_out = cnt;
-    if (sort_on_device && cnt > 0 && !(h_nodes && h_values)) {
-        u32 c2 = 1;
-        while (c2 < cnt) c2 <<= 1;
-        topk_sort_kernel<<<1, 1024, 0, stream>>>(d_nodes, d_out, cnt, c2);
-        *launches += 1;
-    }
-    if (kth_value) {
-        double t = 0.0;
-        if (!hs.all_positive) memcpy(&t, &hs.key_T, sizeof t);
-        *kth_value = t;
-    }
-    if (h_nodes && h_values) {
-        if (cnt > 0) {
-            u32 c2 = 1;
-            while (c2 < cnt) c2 <<= 1;
-            topk_sort_kernel<<<1, 1024, 0, stream>>>(d_nodes, d_out, cnt, c2);
-            *launches += 1;
-            if ((e = cudaMemcpyAsync(h_nodes, d_nodes, sizeof(int32_t) * cnt, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-            if ((e = cudaMemcpyAsync(h_values, d_out, sizeof(double) * cnt, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+__global__ void __launch_bounds__(1024) sel_finish_kernel(SelSlot* st, SelResult* res, const u64* __restrict__ cand_keys,
+                                                           const int32_t* __restrict__ cand_ids, size_t cand_stride,
+                                                           int32_t* out_nodes, double* out_vals, u32 out_stride, u32 k, int sort) {
+    __shared__ u32 h[256];
+    __shared__ u64 sh_prefix;
+    __shared__ u32 sh_rem, sh_eq, sh_idprefix, sh_out;
+    SelSlot& s = st[blockIdx.x];
+    const u64* __restrict__ ck = cand_keys + cand_stride * blockIdx.x;
+    const int32_t* __restrict__ ci = cand_ids + cand_stride * blockIdx.x;
+    int32_t* on = out_nodes + (size_t)out_stride * blockIdx.x;
+    double* ov = out_vals + (size_t)out_stride * blockIdx.x;
+    const u32 m = s.cand_count;
+    u64 T = 0;
+    if (!s.all_positive) {
+        if (threadIdx.x == 0) { sh_prefix = (u64)s.bin << 52; sh_rem = k - s.above; sh_eq = 0; sh_out = s.out_count; }
+        // remaining 52 key bits: six 8-bit digits (bits 51..4), then the last 4 bits
+        for (int pass = 0; pass < 7; ++pass) {
+            const int bits = pass < 6 ? 8 : 4, shift = pass < 6 ? 44 - 8 * pass : 0;
+            const u64 hi_mask = ~0ull << (shift + bits);
+            if (threadIdx.x < 256) h[threadIdx.x] = 0;
+            __syncthreads();
+            const u64 prefix = sh_prefix;
+            for (u32 i = threadIdx.x; i < m; i += blockDim.x) {
+                const u64 key = ck[i];
+                if ((key & hi_mask) == prefix) atomicAdd(&h[(key >> shift) & ((1u << bits) - 1)], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                u32 rem = sh_rem;
+                for (int b = (1 << bits) - 1; b >= 0; --b) {
+                    const u32 c = h[b];
+                    if (c >= rem) { sh_prefix |= (u64)b << shift; sh_eq = c; break; }
+                    rem -= c;
+                }
+                sh_rem = rem; // after the last pass: how many entries equal to the k-th key belong to the top-k
+            }
+            __syncthreads();
         }
-        for (u32 i = cnt; i < k; ++i) { h_nodes[i] = 0; h_values[i] = 0.0; }
+        T = sh_prefix;
+        const u32 need_eq = sh_rem, count_eq = sh_eq;
+        u32 idT = 0xffffffffu;
+        if (need_eq != count_eq) { // ties at the k-th value: the need_eq smallest ids among them (ascending select over 32 bits)
+            if (threadIdx.x == 0) { sh_idprefix = 0; sh_rem = need_eq; }
+            for (int shift = 24; shift >= 0; shift -= 8) {
+                const u32 hi_mask = shift >= 24 ? 0u : (~0u << (shift + 8));
+                if (threadIdx.x < 256) h[threadIdx.x] = 0;
+                __syncthreads();
+                const u32 prefix = sh_idprefix;
+                for (u32 i = threadIdx.x; i < m; i += blockDim.x)
+                    if (ck[i] == T && ((u32)ci[i] & hi_mask) == prefix) atomicAdd(&h[((u32)ci[i] >> shift) & 0xff], 1u);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    u32 rem = sh_rem;
+                    for (int b = 0; b < 256; ++b) {
+                        const u32 c = h[b];
+                        if (c >= rem) { sh_idprefix |= (u32)b << shift; break; }
+                        rem -= c;
+                    }
+                    sh_rem = rem;
+                }
+                __syncthreads();
+            }
+            idT = sh_idprefix;
+        }
+        for (u32 i = threadIdx.x; i < m; i += blockDim.x) {
+            const u64 key = ck[i];
+            const int32_t id = ci[i];
+            if (key > T || (key == T && (u32)id <= idT)) {
+                const u32 pos = atomicAdd(&sh_out, 1u);
+                if (pos < out_stride) { on[pos] = id; ov[pos] = __longlong_as_double((long long)key); }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s.out_count = sh_out;
     }
-    return cudaGetLastError();
+    __syncthreads();
+    const u32 cnt = min(s.out_count, k);
+    if (sort && cnt > 0) {
+        u32 p2 = 1;
+        while (p2 < cnt) p2 <<= 1;
+        bitonic_sort_block(on, ov, cnt, p2);
+    }
+    if (threadIdx.x == 0) {
+        res[blockIdx.x].key_T = s.all_positive ? 0ull : T;
+        res[blockIdx.x].out_count = cnt;
+        res[blockIdx.x].all_positive = s.all_positive;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
