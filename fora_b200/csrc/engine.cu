@@ -98,6 +98,10 @@ struct fora_ctx {
     DevBuf<double> inc;
     DevBuf<u32> eoff;
     DevBuf<u64> block_sum;
+    DevBuf<int32_t> log_v;  // reserve credit log of the push (push.cuh)
+    DevBuf<double> log_r;
+    DevBuf<u32> log_cur;
+    size_t log_cap = 0;
     DevBuf<u64> trace; // FORA_PUSH_TRACE=1: per-level trace of the last push launch
     bool trace_on = false;
     DevBuf<PushCtl> ctl;
@@ -262,6 +266,7 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     cudaDeviceSynchronize();
     free_graph(ctx->g);
     ctx->reserve.release(); ctx->residue.release(); ctx->arena.release(); ctx->front0.release(); ctx->front1.release();
+    ctx->log_v.release(); ctx->log_r.release(); ctx->log_cur.release();
     ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
     ctx->ppr.release(); ctx->ub.release(); ctx->lb.release(); ctx->in_topk.release(); ctx->flags.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
@@ -757,6 +762,15 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         CK(ctx->inc.ensure(fcap));
         CK(ctx->eoff.ensure(fcap + 1));
         CK(ctx->block_sum.ensure(MAX_PUSH_CTAS));
+        // reserve credit log: room for 2n pushes per slot and wave (LJ-shape --balanced queries push ~1.06 n vertices); more spills
+        // into the direct update.  FORA_PUSH_LOG=0 disables the log.
+        CK(ctx->log_cur.ensure(MAX_SLOTS));
+        CK(cudaMemsetAsync(ctx->log_cur.p, 0, sizeof(u32) * MAX_SLOTS, ctx->stream));
+        ctx->log_cap = (getenv("FORA_PUSH_LOG") && atoi(getenv("FORA_PUSH_LOG")) == 0) ? 0 : std::min<size_t>(2 * n, 0xfffffff0u);
+        if (ctx->log_cap) {
+            CK(ctx->log_v.ensure(ctx->log_cap * S));
+            CK(ctx->log_r.ensure(ctx->log_cap * S));
+        }
         ctx->trace_on = getenv("FORA_PUSH_TRACE") != nullptr;
         if (ctx->trace_on) { CK(ctx->trace.ensure(4 * 4096)); CK(cudaMemset(ctx->trace.p, 0, sizeof(u64) * 4 * 4096)); }
         CK(ctx->ctl.ensure(1));
@@ -890,13 +904,28 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     a.trace_cap = ctx->trace_on ? 4096 : 0;
     a.tile_max = getenv("FORA_TILE_MAX") ? (u32)atoi(getenv("FORA_TILE_MAX")) : TILE_MAX;
     a.l2_hints = getenv("FORA_L2_HINTS") ? (u32)atoi(getenv("FORA_L2_HINTS")) : 1u;
+    a.log_v = ctx->log_cap ? ctx->log_v.p : nullptr;
+    a.log_r = ctx->log_r.p;
+    a.log_cap = (u32)ctx->log_cap;
+    a.log_cur = ctx->log_cur.p;
     a.colx = ctx->g.deg_shift ? ctx->g.out_colx : nullptr;
     a.deg_shift = ctx->g.deg_shift;
     return a;
 }
 
-// launch the persistent push kernel over whatever frontier is in front0 / ctl->fcount[0]
-static int launch_push(fora_ctx* ctx) {
+// add the logged reserve credits (alpha * r per push) to the reserve vectors and empty the log
+static int apply_push_log(fora_ctx* ctx) {
+    if (!ctx->log_cap) return FORA_OK;
+    apply_log_kernel<<<dim3(ctx->num_sms * 8, ctx->slots), 256, 0, ctx->stream>>>(ctx->g.n, ctx->p.alpha, ctx->log_cur.p, (u32)ctx->log_cap, ctx->log_v.p,
+                                                                               ctx->log_r.p, ctx->reserve.p);
+    CKL();
+    CK(cudaMemsetAsync(ctx->log_cur.p, 0, sizeof(u32) * MAX_SLOTS, ctx->stream));
+    return FORA_OK;
+}
+
+// launch the persistent push kernel over whatever frontier is in front0 / ctl->fcount[0].  defer_log: leave the reserve
+// credits of this launch in the log (the caller applies them once after the last round of the wave).
+static int launch_push(fora_ctx* ctx, bool defer_log = false) {
     PushArgs a = make_push_args(ctx);
     ctx->level_base += (1u << 20);
     int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
@@ -913,7 +942,7 @@ static int launch_push(fora_ctx* ctx) {
     }
     kev_end(ctx);
     ctx->launches++;
-    return FORA_OK;
+    return defer_log ? FORA_OK : apply_push_log(ctx);
 }
 
 // rsum / nnz of every slot; with seed_next also the seed lists of the next round at h_meta->next_rmax
@@ -953,6 +982,7 @@ static int init_wave(fora_ctx* ctx, int cnt, int seed_source, const int32_t* d_s
     }
     CK(cudaMemsetAsync(ctx->reserve.p, 0, sizeof(double) * n * cnt, ctx->stream));
     CK(cudaMemsetAsync(ctx->residue.p, 0, sizeof(double) * n * cnt, ctx->stream));
+    if (ctx->log_cur.p) CK(cudaMemsetAsync(ctx->log_cur.p, 0, sizeof(u32) * MAX_SLOTS, ctx->stream)); // a new wave starts with an empty credit log
     CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
     push_init_kernel<<<1, MAX_SLOTS, 0, ctx->stream>>>(ctx->g.n, ctx->slots, ctx->meta.p->source, ctx->hot_deg, ctx->reserve.p,
                                                       ctx->residue.p, ctx->front0.p, ctx->ctl.p, seed_source, ctx->meta.p->state);
@@ -963,7 +993,7 @@ static int init_wave(fora_ctx* ctx, int cnt, int seed_source, const int32_t* d_s
 // one resumable round over the slots flagged in h_meta->active (rmax per slot in h_meta->rmax)
 // have_seeds: the previous stats pass already produced this round's seed lists (h_meta->seed_count, front0);
 // next_seed: let this round's stats pass prepare the following round at h_meta->next_rmax
-static int push_round_active(fora_ctx* ctx, bool have_seeds = false, bool next_seed = false) {
+static int push_round_active(fora_ctx* ctx, bool have_seeds = false, bool next_seed = false, bool defer_log = false) {
     SlotMeta* h = ctx->h_meta;
     CK(cudaMemcpyAsync(ctx->meta.p->rmax, h->rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->meta.p->active, h->active, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
@@ -979,7 +1009,7 @@ static int push_round_active(fora_ctx* ctx, bool have_seeds = false, bool next_s
                                                                        ctx->meta.p->active, ctx->front0.p, ctx->ctl.p);
         CKL();
     }
-    int rc = launch_push(ctx);
+    int rc = launch_push(ctx, defer_log);
     if (rc) return rc;
     return launch_residue_stats(ctx, next_seed);
 }
@@ -1027,7 +1057,7 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
         if (!any) break;
         // the stats pass of this round also lists the seeds of the next one (rmax/2) for every active slot
         for (int s = 0; s < MAX_SLOTS; ++s) h->next_rmax[s] = (s < cnt && h->active[s]) ? rmax[s] / 2 : 0.0;
-        if ((rc = push_round_active(ctx, iter > 0, true))) return rc;
+        if ((rc = push_round_active(ctx, iter > 0, true, true))) return rc; // reserve credits stay logged until the last round
         if ((rc = meta_d2h_sync(ctx))) return rc;
         for (int s = 0; s < cnt; ++s) {
             if (!h->active[s]) continue;
@@ -1040,7 +1070,7 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
     }
     for (int s = 0; s < cnt; ++s)
         if (!done[s]) final_rmax[s] = rmax[s] * 2;
-    return FORA_OK;
+    return apply_push_log(ctx); // one pass per wave: a vertex pushed in several rounds costs one sector round trip, not several
 }
 
 // Walk phase of a wave: plan + walk kernels; ppr is accumulated in place into `ppr` ([slots*n],

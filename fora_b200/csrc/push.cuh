@@ -91,6 +91,12 @@ struct PushArgs {
     u32 l2_hints;                        // 1: evict_last on residue atomics / degree loads, evict_first on streams
     const int32_t* __restrict__ colx;    // optional packed columns: id | min(d_out(id), dmax) << deg_shift (null: plain g.col)
     u32 deg_shift;                       // id bits of a packed column entry; the remaining high bits hold the out-degree code
+    // reserve credit log: phase A appends (vertex, residue pushed) instead of the random read-modify-write of reserve[v];
+    // apply_log_kernel adds alpha*r slot by slot later (engine.cu).  Entries that do not fit take the direct update.
+    int32_t* log_v;                      // [slots*log_cap], null: no log
+    double* log_r;                       // [slots*log_cap]
+    u32 log_cap;
+    u32* log_cur;                        // [MAX_SLOTS] entries logged so far in this wave, per slot
 };
 
 // dynamic shared memory of the push kernel (~70 KB, two CTAs per SM)
@@ -107,6 +113,8 @@ struct PushSmem {
     int32_t source[MAX_SLOTS];
     u32 cnt_edges[MAX_SLOTS], cnt_verts[MAX_SLOTS];
     u32 fbase[MAX_SLOTS + 1];    // the level's frontier = the slots' segments concatenated in slot order
+    u32 logbase[MAX_SLOTS];      // log position of the first frontier entry of each slot at this level
+    u32 prevcnt[MAX_SLOTS];      // frontier size of each slot at this level (advances logbase at the next one)
     u32 i0;
     u32 step_ctr;                // dynamic hand-out of 32*PUSH_UB-edge steps inside a batch
 };
@@ -186,7 +194,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
         const u32 i0 = b0 + threadIdx.x * PUSH_UA;
         u64 e[PUSH_UA];
         double r[PUSH_UA], rs[PUSH_UA];
-        u32 d[PUSH_UA];
+        u32 d[PUSH_UA], lp[PUSH_UA];
 #pragma unroll
         for (int k = 0; k < PUSH_UA; ++k) e[k] = (i0 + k < hi_i) ? frontier_entry(a, sm, cur, i0 + k) : ~0ull;
 #pragma unroll
@@ -194,9 +202,14 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             r[k] = rs[k] = 0.0;
             d[k] = 0;
             if (e[k] != ~0ull) {
-                const size_t gi = (size_t)entry_slot(e[k]) * a.n + (u32)e[k];
+                const int slot = entry_slot(e[k]);
+                const size_t gi = (size_t)slot * a.n + (u32)e[k];
                 r[k] = __ldcg(&a.residue[gi]);
-                rs[k] = __ldcg(&a.reserve[gi]);
+                lp[k] = sm.logbase[slot] + (i0 + k - sm.fbase[slot]);
+                if (!(a.log_v && lp[k] < a.log_cap)) {
+                    lp[k] = 0xffffffffu; // no room (or no log): direct update of the reserve
+                    rs[k] = __ldcg(&a.reserve[gi]);
+                }
                 d[k] = entry_deg24(e[k]);
                 if (d[k] == DEG_SAT) d[k] = (u32)__ldg(&a.deg[(u32)e[k]]);
             }
@@ -210,8 +223,17 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             if (e[k] == ~0ull) continue;
             const int slot = entry_slot(e[k]);
             const size_t gi = (size_t)slot * a.n + (u32)e[k];
-            a.residue[gi] = 0.0;
-            a.reserve[gi] = rs[k] + r[k] * a.alpha;
+            // The zero must not leave before the load of the same word has returned: a store that reaches the L2 while the
+            // sector's fill is still pending takes a slow path (measured: phase A 3x slower when the compiler hoisted a plain
+            // `= 0.0` right behind the load).  0.0 * r (r finite, >= 0) makes the store data-dependent on the load.
+            a.residue[gi] = __dmul_rn(r[k], 0.0);
+            if (lp[k] != 0xffffffffu) {
+                const size_t li = (size_t)slot * a.log_cap + lp[k];
+                a.log_v[li] = (int32_t)(u32)e[k];
+                a.log_r[li] = r[k];
+            } else {
+                a.reserve[gi] = rs[k] + r[k] * a.alpha;
+            }
             a.inc[i0 + k] = d[k] ? ((1.0 - a.alpha) * r[k]) / (double)d[k] : r[k] * (1.0 - a.alpha);
             loc[k] = esum; // thread-local exclusive offset, completed below
             esum += d[k] ? d[k] : 1u;
@@ -472,6 +494,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         sm.source[i] = i < a.slots ? a.source[i] : 0;
         sm.cnt_edges[i] = 0;
         sm.cnt_verts[i] = 0;
+        sm.logbase[i] = (a.log_v && i < a.slots) ? a.log_cur[i] : 0u;
+        sm.prevcnt[i] = 0;
     }
     __syncthreads();
 
@@ -483,8 +507,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
             const u32 c1 = l + WARP < a.slots ? *((volatile u32*)&ctl->fcount[level % 3][l + WARP]) : 0u;
             const u32 i0 = warp_incl_scan(c0);
             const u32 i1 = warp_incl_scan(c1) + __shfl_sync(FULL, i0, 31);
-            if (l < a.slots) sm.fbase[l] = i0 - c0;
-            if (l + WARP < a.slots) sm.fbase[l + WARP] = i1 - c1;
+            if (l < a.slots) { sm.fbase[l] = i0 - c0; sm.logbase[l] += sm.prevcnt[l]; sm.prevcnt[l] = c0; }
+            if (l + WARP < a.slots) { sm.fbase[l + WARP] = i1 - c1; sm.logbase[l + WARP] += sm.prevcnt[l + WARP]; sm.prevcnt[l + WARP] = c1; }
             if (l == 31) sm.fbase[a.slots] = i1;
         }
         __syncthreads();
@@ -515,6 +539,21 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         push_phase_b<OffT>(a, g, sm, cur, nf, level, blockIdx.x, gridDim.x, nxt, nxt_count);
         grid.sync();
     }
+    // every CTA holds the same log positions; CTA 0 publishes them for the next launch of the wave / the apply pass
+    if (a.log_v && blockIdx.x == 0 && threadIdx.x < (u32)a.slots) a.log_cur[threadIdx.x] = sm.logbase[threadIdx.x] + sm.prevcnt[threadIdx.x];
+}
+
+// reserve[v] += alpha * r for every logged push; grid.y = slot, so the grid works through the slots one after another
+// and each slot's 8n-byte reserve vector is L2-resident while its REDs land.
+__global__ void __launch_bounds__(256) apply_log_kernel(int32_t n, double alpha, const u32* __restrict__ log_cur, u32 cap,
+                                                         const int32_t* __restrict__ log_v, const double* __restrict__ log_r,
+                                                         double* __restrict__ reserve) {
+    const int slot = blockIdx.y;
+    const u32 cnt = min(log_cur[slot], cap);
+    const int32_t* __restrict__ lv = log_v + (size_t)slot * cap;
+    const double* __restrict__ lr = log_r + (size_t)slot * cap;
+    double* res = reserve + (size_t)slot * n;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) atomicAdd(&res[__ldcs(&lv[i])], __ldcs(&lr[i]) * alpha);
 }
 
 // ---------------------------------------------------------------------------------------------
