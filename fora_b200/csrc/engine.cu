@@ -767,6 +767,7 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         CK(ctx->log_cur.ensure(MAX_SLOTS));
         CK(cudaMemsetAsync(ctx->log_cur.p, 0, sizeof(u32) * MAX_SLOTS, ctx->stream));
         ctx->log_cap = (getenv("FORA_PUSH_LOG") && atoi(getenv("FORA_PUSH_LOG")) == 0) ? 0 : std::min<size_t>(2 * n, 0xfffffff0u);
+        if (ctx->log_cap && getenv("FORA_PUSH_LOG_CAP")) ctx->log_cap = std::max<size_t>(1, (size_t)atoll(getenv("FORA_PUSH_LOG_CAP"))); // test hook: force overflow
         if (ctx->log_cap) {
             CK(ctx->log_v.ensure(ctx->log_cap * S));
             CK(ctx->log_r.ensure(ctx->log_cap * S));

@@ -26,7 +26,7 @@ SLOTS = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 NQ = int(sys.argv[2]) if len(sys.argv) > 2 else 96
 KNOBS = ("FORA_L2_FETCH", "FORA_PUSH_PACK", "FORA_RELABEL_KEY", "FORA_WALK_HOT_MB", "FORA_L2_HINTS", "FORA_NO_WALK_PIN",
          "FORA_COST_WALK", "FORA_COST_EDGE", "FORA_COST_VERTEX", "FORA_TILE_MAX", "FORA_WALK_GRID", "FORA_WALK_V", "FORA_WALK_HOT_KEEP",
-         "FORA_PUSH_V", "FORA_PUSH_DYN", "FORA_DEBUG_NO_RED", "FORA_WALK_PIN_PPR")
+         "FORA_PUSH_V", "FORA_PUSH_DYN", "FORA_DEBUG_NO_RED", "FORA_WALK_PIN_PPR", "FORA_PUSH_LOG", "FORA_PUSH_LOG_CAP")
 
 n, m = 4847571, 68993773
 t0 = time.time()

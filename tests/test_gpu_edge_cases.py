@@ -107,6 +107,9 @@ def test_max_slots_and_ragged_last_wave():
     {"FORA_NO_RELABEL": "1"},                       # no relabelling at all
     {"FORA_WALK_HOT_MB": "0.01"},                   # evict_first instantiation of the walk kernel on a small graph
     {"FORA_WALK_HOT_MB": "0"},                      # unhinted instantiation
+    {"FORA_PUSH_LOG": "0"},                         # reserve credited directly in phase A, no log
+    {"FORA_PUSH_LOG_CAP": "37"},                    # a log of 37 entries per slot: almost every push overflows into the direct update
+    {"FORA_PUSH_LOG_CAP": "2500"},                  # the log fills up in the middle of a push
 ])
 def test_layout_variants_give_the_same_answers(env, monkeypatch):
     """Packed columns, relabelling keys and L2 hints are layout choices: push results must match the schedule-matched
@@ -127,10 +130,12 @@ def test_layout_variants_give_the_same_answers(env, monkeypatch):
         r2 = O.push_sync(s, rmax, 1, 0)
         a, b = O.fwd()
         assert relerr(res, a) < 1e-9 and relerr(rsd, b) < 1e-9 and abs(rsum - r2) < 1e-12
-    ppr, st, _ = E.query_batch("fora", np.array([hub, 17, 4000], np.int32))
-    for i, s in enumerate((hub, 17, 4000)):
-        exact = O.power_iteration(int(s), 150)
-        big = exact >= 1.0 / g.n
-        assert abs(ppr[i].sum() - 1.0) < 1e-9
-        assert (np.abs(ppr[i][big] - exact[big]) / exact[big]).max() < 0.5
+    for balanced in (0, 1):  # balanced: several push rounds per wave, the credit log is applied once after the last one
+        E.configure("fora", 0.5, opt=1, balanced=balanced)
+        ppr, st, _ = E.query_batch("fora", np.array([hub, 17, 4000], np.int32))
+        for i, s in enumerate((hub, 17, 4000)):
+            exact = O.power_iteration(int(s), 150)
+            big = exact >= 1.0 / g.n
+            assert abs(ppr[i].sum() - 1.0) < 1e-9
+            assert (np.abs(ppr[i][big] - exact[big]) / exact[big]).max() < 0.5
     E.close()
