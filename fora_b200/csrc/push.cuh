@@ -204,7 +204,11 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             if (e[k] != ~0ull) {
                 const int slot = entry_slot(e[k]);
                 const size_t gi = (size_t)slot * a.n + (u32)e[k];
-                r[k] = __ldcg(&a.residue[gi]);
+                // read + zero in ONE L2 operation.  (A load followed by a plain `= 0.0` store is a trap: when the compiler hoists
+                // the store right behind the load, it reaches the L2 while the sector's fill is still pending and takes a slow
+                // path -- phase A ran 3x slower.  Ordering the store behind the load by a data dependency fixed that; the
+                // exchange is 1.4 % faster still.)
+                r[k] = __longlong_as_double((long long)atomicExch((unsigned long long*)&a.residue[gi], 0ull));
                 lp[k] = sm.logbase[slot] + (i0 + k - sm.fbase[slot]);
                 if (!(a.log_v && lp[k] < a.log_cap)) {
                     lp[k] = 0xffffffffu; // no room (or no log): direct update of the reserve
@@ -223,10 +227,6 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             if (e[k] == ~0ull) continue;
             const int slot = entry_slot(e[k]);
             const size_t gi = (size_t)slot * a.n + (u32)e[k];
-            // The zero must not leave before the load of the same word has returned: a store that reaches the L2 while the
-            // sector's fill is still pending takes a slow path (measured: phase A 3x slower when the compiler hoisted a plain
-            // `= 0.0` right behind the load).  0.0 * r (r finite, >= 0) makes the store data-dependent on the load.
-            a.residue[gi] = __dmul_rn(r[k], 0.0);
             if (lp[k] != 0xffffffffu) {
                 const size_t li = (size_t)slot * a.log_cap + lp[k];
                 a.log_v[li] = (int32_t)(u32)e[k];
