@@ -222,14 +222,8 @@ extern "C" int fora_ctx_create(int device, uint64_t seed, fora_ctx** out) {
     ctx->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
     ctx->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
     ctx->l2_policy = getenv("FORA_NO_L2_POLICY") == nullptr && ctx->l2_persist_max > 0;
-    // DRAM->L2 fill granularity (32 / 64 / 128 bytes, a device-wide hint).  Every hot access of this engine is a
-    // random 4- or 8-byte access, so anything fetched beyond the 32-byte sector is wasted DRAM bandwidth.
-    if (getenv("FORA_L2_FETCH")) {
-        const cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(getenv("FORA_L2_FETCH")));
-        size_t got = 0;
-        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
-        if (getenv("FORA_VERBOSE")) fprintf(stderr, "[fora] L2 fetch granularity: asked %s, %s, now %zu\n", getenv("FORA_L2_FETCH"), cudaGetErrorString(le), got);
-    }
+    // (cudaLimitMaxL2FetchGranularity 32 / 64 / 128 was measured to have no effect on B200 for this engine's random 4- and
+    // 8-byte accesses -- profiles/r1_ubench_l2_fetch_granularity.txt -- so it is left at the driver's default.)
     if (!prop.cooperativeLaunch) {
         g_create_error = "device lacks cooperative launch";
         delete ctx;

@@ -85,7 +85,7 @@ def group(title, base, candidates):
 
 PLAN = sys.argv[3] if len(sys.argv) > 3 else "b"
 env = {}
-if PLAN == "a":  # first sweep (all knobs off by default then)
+if PLAN == "a":  # first sweep of the session, kept for the record (FORA_L2_FETCH no longer exists in the engine: no effect)
     OFF = {"FORA_PUSH_PACK": 0, "FORA_RELABEL_KEY": 0, "FORA_TILE_MAX": 16384, "FORA_WALK_GRID": 8}
     env = group("L2 fill granularity", OFF, [("fetch32", dict(OFF, FORA_L2_FETCH=32)), ("fetch128", dict(OFF, FORA_L2_FETCH=128)),
                                               ("fetch64", dict(OFF, FORA_L2_FETCH=64))])
