@@ -5,7 +5,8 @@
 // (reserve += alpha*r; every out-neighbour += ((1-alpha)*r)/d_out; dangling mass -> source;
 // push while residue/d_out >= rmax) on a level-synchronous schedule:
 //
-//   level k, phase A  every frontier vertex reads and zeroes its residue, credits its reserve
+//   level k, phase A  every frontier vertex reads and zeroes its residue (one exchange) and logs its reserve credit
+//                     (vertex, r); apply_log_kernel adds alpha*r to the reserve vectors once per wave
 //            phase B  all scatters land as fp64 atomics; a vertex joins level k+1 exactly when one
 //                     atomic moves its residue across rmax*d_out (detected from the value the
 //                     atomic returns, so no per-vertex flag array and no per-level scan)
@@ -14,8 +15,9 @@
 // frontier test and termination live on the device.  Work is edge-balanced across the grid: the
 // edges of a level are laid on one slot-major line (exclusive scan of the frontier's out-degrees) and
 // cut into tiles that the CTAs take round-robin, so a power-law hub is simply split across CTAs, no
-// warp waits for a straggler, and the grid sweeps one or two slots' residue vectors at a time (they stay
-// L2-resident although a wave holds many slots and all slots share each level's two barriers).
+// warp waits for a straggler, and the grid sweeps the slots front to back (all slots share each level's two
+// barriers; with tens of slots their vectors do not stay L2-resident between levels -- the kernel runs at the
+// memory system's random read-modify-write rate).
 #pragma once
 #include <cooperative_groups.h>
 

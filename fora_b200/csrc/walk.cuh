@@ -8,11 +8,10 @@
 //             N = (ull)(omega*rsum)  -- the reference's expressions, evaluated in the same order in
 //             IEEE double on the device (query.h:270,314-317; opt: 349,363-370), compacted in
 //             ascending vertex order with an exclusive prefix sum of n_v (two deterministic passes)
-//   walk      one walker per thread; a thread that finishes a walk immediately starts its next one
-//             (lanes never idle waiting for the longest walk of the warp); Philox4x32-10 keyed by
-//             (seed, query id, round) with counter (walk index within source, draw block, source),
-//             so destinations do not depend on scheduling, slot count or GPU count; row offsets and
-//             neighbours through the read-only path; ppr[dest] += inc_v as fp64 RED.
+//   walk      one walker per thread in a warp-converged loop (refill together, one Philox block = two steps together);
+//             Philox4x32-10 keyed by (seed, query id, round) with counter (walk index within source, draw block,
+//             source), so destinations do not depend on scheduling, chunk size, slot count or GPU count; row offsets
+//             and neighbours through the read-only path; ppr[dest] += inc_v as fp64 RED.
 #pragma once
 #include "common.cuh"
 
@@ -265,7 +264,7 @@ struct WalkArgs {
 // step first stops with probability alpha (skipped once when NO_ZERO_HOP), then moves to a uniform
 // out-neighbour, or back to THIS walk's start when the current vertex is dangling.
 //
-// Per CTA chunk of WALK_CHUNK walks: (1) the prefix of the sources touching the chunk is staged in shared
+// Per CTA chunk of up to WALK_CHUNK walks (walk_chunk_size): (1) the prefix of the sources touching the chunk is staged in shared
 // memory, (2) a divergence-free expansion pass resolves the owner source of every walk of the chunk
 // (binary search, all lanes busy), (3) lanes fetch walks dynamically from a shared counter -- a lane that
 // finishes a walk immediately starts the next one -- and advance two steps per Philox block (one
