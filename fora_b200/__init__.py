@@ -55,6 +55,34 @@ class BatchTiming(C.Structure):
 
 
 _lib = None
+_host = None
+HOST_LIB_PATH = os.path.join(_HERE, "libfora_host.so")
+
+
+def _bind_host(L):
+    L.fora_host_read_attribute.argtypes = [C.c_char_p, c_ip, c_lp]
+    L.fora_host_read_edges.restype = C.c_int64
+    L.fora_host_read_edges.argtypes = [C.c_char_p, C.c_int32, c_ip, c_ip]
+    L.fora_host_csr_from_edges.argtypes = [C.c_int32, C.c_int64, c_ip, c_ip, c_lp, c_ip, c_lp, c_ip]
+    L.fora_host_synth_edges.restype = C.c_int64
+    L.fora_host_synth_edges.argtypes = [C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_double, c_ip, c_ip]
+    L.fora_host_setting.argtypes = [C.c_int, C.c_int32, C.c_int64] + [C.c_double] * 4 + [C.c_int, C.c_double, c_dp, c_dp]
+    return L
+
+
+def host_lib():
+    """The host-only helpers of the ABI (loader, CSR from edges, synthetic graphs, *_setting): libfora_host.so, the same
+    host_util.cpp without the GPU engine -- what a process that must not map the engine uses (bench.py --impl reference).
+    A process that has already loaded libfora_b200.so uses that copy."""
+    global _host
+    if _host is None:
+        if _lib is not None:
+            _host = _lib
+        elif os.path.exists(HOST_LIB_PATH):
+            _host = _bind_host(C.CDLL(HOST_LIB_PATH))
+        else:
+            _host = lib()
+    return _host
 
 
 def lib():
@@ -64,15 +92,8 @@ def lib():
         return _lib
     if not os.path.exists(LIB_PATH):
         raise ForaError("%s is missing: build it with `make -C fora_b200` (there is no CPU fallback)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+    L = _bind_host(C.CDLL(LIB_PATH))
     vp = C.c_void_p
-    L.fora_host_read_attribute.argtypes = [C.c_char_p, c_ip, c_lp]
-    L.fora_host_read_edges.restype = C.c_int64
-    L.fora_host_read_edges.argtypes = [C.c_char_p, C.c_int32, c_ip, c_ip]
-    L.fora_host_csr_from_edges.argtypes = [C.c_int32, C.c_int64, c_ip, c_ip, c_lp, c_ip, c_lp, c_ip]
-    L.fora_host_synth_edges.restype = C.c_int64
-    L.fora_host_synth_edges.argtypes = [C.c_int32, C.c_int64, C.c_uint64, C.c_double, C.c_double, c_ip, c_ip]
-    L.fora_host_setting.argtypes = [C.c_int, C.c_int32, C.c_int64] + [C.c_double] * 4 + [C.c_int, C.c_double, c_dp, c_dp]
     L.fora_ctx_create.argtypes = [C.c_int, C.c_uint64, C.POINTER(vp)]
     L.fora_ctx_destroy.argtypes = [vp]
     L.fora_last_error.restype = C.c_char_p
@@ -80,6 +101,7 @@ def lib():
     L.fora_ctx_set_stream.argtypes = [vp, vp]
     L.fora_ctx_set_slots.argtypes = [vp, C.c_int]
     L.fora_ctx_sync.argtypes = [vp]
+    L.fora_ctx_set_query_base.argtypes = [vp, C.c_uint64]
     L.fora_graph_upload.argtypes = [vp, C.c_int32, C.c_int64, c_lp, c_ip, c_lp, c_ip]
     L.fora_graph_build_from_edges.argtypes = [vp, C.c_int32, C.c_int64, c_ip, c_ip, C.c_int64, C.c_int]
     L.fora_graph_download_csr.argtypes = [vp, c_lp, c_ip, c_lp, c_ip]
@@ -121,14 +143,14 @@ def _p(a, t):
 # ------------------------------------------------------------------------------- host helpers
 def read_attribute(path):
     n, m = C.c_int32(0), C.c_int64(0)
-    rc = lib().fora_host_read_attribute(path.encode(), C.byref(n), C.byref(m))
+    rc = host_lib().fora_host_read_attribute(path.encode(), C.byref(n), C.byref(m))
     if rc:
         raise ForaError("cannot read %s (rc=%d)" % (path, rc))
     return n.value, m.value
 
 
 def read_edges(path, n):
-    L = lib()
+    L = host_lib()
     cnt = L.fora_host_read_edges(path.encode(), n, None, None)
     if cnt < 0:
         raise ForaError("cannot read %s (rc=%d)" % (path, cnt))
@@ -144,7 +166,7 @@ def csr_from_edges(n, src, dst, with_in=True):
     out_ptr, out_col = np.empty(n + 1, np.int64), np.empty(max(kept, 1), np.int32)
     in_ptr = np.empty(n + 1, np.int64) if with_in else None
     in_col = np.empty(max(kept, 1), np.int32) if with_in else None
-    rc = lib().fora_host_csr_from_edges(n, len(src), _p(src, c_ip), _p(dst, c_ip), _p(out_ptr, c_lp), _p(out_col, c_ip),
+    rc = host_lib().fora_host_csr_from_edges(n, len(src), _p(src, c_ip), _p(dst, c_ip), _p(out_ptr, c_lp), _p(out_col, c_ip),
                                         _p(in_ptr, c_lp), _p(in_col, c_ip))
     if rc:
         raise ForaError("csr_from_edges rc=%d" % rc)
@@ -155,7 +177,7 @@ def csr_from_edges(n, src, dst, with_in=True):
 
 def synth_edges(n, m, seed=42, exponent=2.3, dangling_frac=0.03):
     src, dst = np.empty(m, np.int32), np.empty(m, np.int32)
-    rc = lib().fora_host_synth_edges(n, m, seed, exponent, dangling_frac, _p(src, c_ip), _p(dst, c_ip))
+    rc = host_lib().fora_host_synth_edges(n, m, seed, exponent, dangling_frac, _p(src, c_ip), _p(dst, c_ip))
     if rc < 0:
         raise ForaError("synth_edges rc=%d" % rc)
     return src, dst
@@ -166,7 +188,7 @@ def setting(which, n, m, epsilon, delta=None, pfail=None, alpha=0.2, opt=0, rmax
     delta = 1.0 / n if delta is None else delta
     pfail = 1.0 / n if pfail is None else pfail
     rmax, omega = C.c_double(0), C.c_double(0)
-    rc = lib().fora_host_setting(SETTING[which], n, m, epsilon, delta, pfail, alpha, opt, rmax_scale, C.byref(rmax), C.byref(omega))
+    rc = host_lib().fora_host_setting(SETTING[which], n, m, epsilon, delta, pfail, alpha, opt, rmax_scale, C.byref(rmax), C.byref(omega))
     if rc:
         raise ForaError("setting rc=%d" % rc)
     return rmax.value, omega.value
@@ -211,6 +233,10 @@ class Engine:
 
     def sync(self):
         self._ck(self.L.fora_ctx_sync(self.h))
+
+    def set_query_base(self, first_query_index):
+        """global list index of the first query of the next batch call (Philox key), see include/fora_b200.h"""
+        self._ck(self.L.fora_ctx_set_query_base(self.h, int(first_query_index)))
 
     # --- graph
     def upload_graph(self, n, m_decl, out_ptr, out_col, in_ptr=None, in_col=None):

@@ -30,8 +30,9 @@ struct BwdArgs {
     const u64* __restrict__ counts;     // walk destination histogram of the query, may be null
     double* scratch_res;                // [nblocks*n] dense residue, all zero between targets
     double* scratch_rv;                 // [nblocks*n] residue snapshot per frontier entry
-    int32_t* lists;                     // [nblocks*4*n] touched (2n) | cur (n) | nxt (n)
-    int32_t* overflow;                  // [1] set if a touched list overflowed (results invalid)
+    int32_t* lists;                     // [nblocks*4*n] touched (n) | stamp (n) | cur (n) | nxt (n)
+    int32_t* overflow;                  // [1] set if a touched list overflowed (cannot happen: one entry per vertex; kept as a guard)
+    u32 epoch_base;                     // stamp value of target t_begin; target t uses epoch_base + (t - t_begin), never 0
     double* ppr;                        // [n] out, may be null
     int32_t t_begin, t_end;             // targets handled by this launch
     double* full_reserve;               // test hook: dense reserve of the single target, may be null
@@ -47,16 +48,22 @@ __global__ void __launch_bounds__(BWD_THREADS) bippr_kernel(BwdArgs<OffT> a) {
     const size_t n = (size_t)a.n;
     double* res = a.scratch_res + n * blockIdx.x;
     double* rv = a.scratch_rv + n * blockIdx.x;
+    // touched list: every vertex whose residue became non-zero for this target, listed ONCE -- stamp[v] holds the epoch of the
+    // last target that listed v, so a frontier vertex that is zeroed in phase A and hit again in phase B is not re-appended
+    // (it used to be: the list then grew with the sum of the frontier sizes over all levels and could overflow at small r_max).
     int32_t* touched = a.lists + 4 * n * blockIdx.x;
+    u32* stamp = (u32*)(touched + n);
     int32_t* cur = touched + 2 * n;
     int32_t* nxt = cur + n;
     const int lane = lane_id(), w = threadIdx.x >> 5;
     u64 my_edges = 0;
 
     for (int32_t t = a.t_begin + blockIdx.x; t < a.t_end; t += gridDim.x) {
+        const u32 ep = a.epoch_base + (u32)(t - a.t_begin);
         if (threadIdx.x == 0) {
             res[t] = 1.0; // init_residual (algo.h:718)
             touched[0] = t;
+            stamp[t] = ep;
             cur[0] = t;
             s_cnt[0] = 1;
             s_cnt[1] = (1.0 < a.rmax) ? 0 : 1; // algo.h:725: the first popped vertex stops the loop if below rmax
@@ -92,7 +99,7 @@ __global__ void __launch_bounds__(BWD_THREADS) bippr_kernel(BwdArgs<OffT> a) {
                         u = a.in_col[b + (OffT)e];
                         const double inc = residual / (double)a.out_deg[u];
                         const double old = atomicAdd_block(&res[u], inc);
-                        first = old == 0.0; // (re-)enters the touched list; duplicates are harmless, see the final sum
+                        if (old == 0.0) first = atomicExch_block(&stamp[u], ep) != ep; // enters the touched list once per target
                         cross = !(old > a.rmax) && (old + inc > a.rmax);
                     }
                     const u32 mf = __ballot_sync(FULL, first), mc = __ballot_sync(FULL, cross);
@@ -102,7 +109,7 @@ __global__ void __launch_bounds__(BWD_THREADS) bippr_kernel(BwdArgs<OffT> a) {
                         base = __shfl_sync(FULL, base, 0);
                         if (first) {
                             const size_t pos = (size_t)base + __popc(mf & lanemask_lt());
-                            if (pos < 2 * n) touched[pos] = u;
+                            if (pos < n) touched[pos] = u;
                             else *a.overflow = 1;
                         }
                     }
@@ -122,8 +129,8 @@ __global__ void __launch_bounds__(BWD_THREADS) bippr_kernel(BwdArgs<OffT> a) {
             int32_t* tmp = cur; cur = nxt; nxt = tmp;
             __syncthreads();
         }
-        // combine and clean: every touched entry is read-and-zeroed exactly once (duplicates then read 0)
-        const int nt = min(s_cnt[0], (int)min((size_t)0x7fffffff, 2 * n));
+        // combine and clean: every touched entry is read-and-zeroed exactly once
+        const int nt = min(s_cnt[0], (int)n);
         double part = 0.0;
         if (!a.keep_residue) {
             for (int i = threadIdx.x; i < nt; i += BWD_THREADS) {

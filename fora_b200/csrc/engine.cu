@@ -142,6 +142,7 @@ struct fora_ctx {
     DevBuf<double> bwd_res, bwd_rv;
     DevBuf<int32_t> bwd_lists;
     int bwd_blocks = 0;
+    u32 bwd_epoch = 1; // next unused stamp value of the backward push's touched lists (bippr.cuh)
     DevBuf<u64> scratch64;
     DevBuf<int32_t> scratch32;
     DevBuf<double> scratchd;
@@ -154,6 +155,7 @@ struct fora_ctx {
     u64 push_kernel_launches = 0, walk_kernel_launches = 0;
     u32 level_base = 0;
     u64 launches = 0;
+    u64 qid_base = 0; // global index of the first query of the next batch call (Philox key); see fora_ctx_set_query_base
     // resumable push session (fora_push_begin / fora_push_round)
     int32_t session_source = -1;
 
@@ -289,6 +291,14 @@ extern "C" int fora_ctx_set_slots(fora_ctx* ctx, int slots) {
     ctx->slots = slots;
     return FORA_OK;
 }
+// Philox streams are keyed by (ctx seed, GLOBAL query index): a caller that shards a query list over GPUs or issues it in
+// several batch calls sets the index of the first query of the next call here, so that no two queries of a run share a
+// random stream and results do not depend on how the list was cut.  Sticky until changed.
+extern "C" int fora_ctx_set_query_base(fora_ctx* ctx, uint64_t first_query_index) {
+    if (!ctx) return FORA_EINVAL;
+    ctx->qid_base = first_query_index;
+    return FORA_OK;
+}
 extern "C" int fora_ctx_sync(fora_ctx* ctx) {
     if (!ctx) return FORA_EINVAL;
     CK(cudaSetDevice(ctx->device));
@@ -306,10 +316,31 @@ __global__ void degree_kernel(int32_t n, const int64_t* __restrict__ ptr, int32_
     }
 }
 
+// a CSR handed in by the caller is checked once on the device: offsets non-decreasing from 0, ids in [0, n)
+__global__ void csr_check_kernel(int32_t n, int64_t ne, const int64_t* __restrict__ ptr, const int32_t* __restrict__ col, int* __restrict__ bad) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t v = t0; v < n; v += stride)
+        if (ptr[v] > ptr[v + 1] || (v == 0 && ptr[0] != 0)) *bad = 1;
+    for (int64_t e = t0; e < ne; e += stride)
+        if ((u32)col[e] >= (u32)n) *bad = 2;
+}
+
+static int graph_upload_impl(fora_ctx* ctx, int32_t n, int64_t m_decl, const int64_t* out_ptr, const int32_t* out_col,
+                             const int64_t* in_ptr, const int32_t* in_col);
 extern "C" int fora_graph_upload(fora_ctx* ctx, int32_t n, int64_t m_decl, const int64_t* out_ptr, const int32_t* out_col,
                                  const int64_t* in_ptr, const int32_t* in_col) {
     if (!ctx) return FORA_EINVAL;
+    const int rc = graph_upload_impl(ctx, n, m_decl, out_ptr, out_col, in_ptr, in_col);
+    if (rc) { // never leave a half-initialised graph behind
+        cudaStreamSynchronize(ctx->stream);
+        free_graph(ctx->g);
+    }
+    return rc;
+}
+static int graph_upload_impl(fora_ctx* ctx, int32_t n, int64_t m_decl, const int64_t* out_ptr, const int32_t* out_col,
+                             const int64_t* in_ptr, const int32_t* in_col) {
     if (n <= 0 || !out_ptr || !out_col) return ctx->fail(FORA_EINVAL, "graph_upload: n>0 and out-CSR required");
+    if (out_ptr[0] != 0 || out_ptr[n] < 0) return ctx->fail(FORA_EINVAL, "graph_upload: out_ptr must start at 0 and be non-negative");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     free_graph(ctx->g);
@@ -325,24 +356,36 @@ extern "C" int fora_graph_upload(fora_ctx* ctx, int32_t n, int64_t m_decl, const
     if (g.off32) CK(cudaMalloc((void**)&g.out_ptr32, sizeof(u32) * (size_t)(n + 1)));
     CK(cudaMemcpyAsync(g.out_ptr64, out_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(g.out_col, out_col, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
-    degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.out_ptr64, g.deg, g.out_ptr32);
+    DevBuf<int> bad;
+    CK(bad.ensure(1));
+    CK(cudaMemsetAsync(bad.p, 0, sizeof(int), ctx->stream));
+    csr_check_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, g.n_edges, g.out_ptr64, g.out_col, bad.p);
     CKL();
     if (in_ptr && in_col) {
-        if (in_ptr[n] != g.n_edges) return ctx->fail(FORA_EINVAL, "graph_upload: in-CSR edge count differs from out-CSR");
+        if (in_ptr[0] != 0 || in_ptr[n] != g.n_edges) { bad.release(); return ctx->fail(FORA_EINVAL, "graph_upload: in-CSR edge count differs from out-CSR"); }
         CK(cudaMalloc((void**)&g.in_ptr64, sizeof(int64_t) * (size_t)(n + 1)));
         CK(cudaMalloc((void**)&g.in_col, sizeof(int32_t) * std::max<size_t>(ne, 1)));
         if (g.off32) CK(cudaMalloc((void**)&g.in_ptr32, sizeof(u32) * (size_t)(n + 1)));
         CK(cudaMemcpyAsync(g.in_ptr64, in_ptr, sizeof(int64_t) * (size_t)(n + 1), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(g.in_col, in_col, sizeof(int32_t) * ne, cudaMemcpyHostToDevice, ctx->stream));
-        if (g.off32) {
-            DevBuf<int32_t> tmp;
-            CK(tmp.ensure((size_t)n));
-            degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.in_ptr64, tmp.p, g.in_ptr32);
-            CKL();
-            CK(cudaStreamSynchronize(ctx->stream));
-            tmp.release();
-        }
+        csr_check_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n, g.n_edges, g.in_ptr64, g.in_col, bad.p);
+        CKL();
         g.has_in = true;
+    }
+    int hbad = 0;
+    CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    bad.release();
+    if (hbad) return ctx->fail(FORA_EINVAL, hbad == 1 ? "graph_upload: row offsets are not non-decreasing" : "graph_upload: a column id lies outside [0, n)");
+    degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.out_ptr64, g.deg, g.out_ptr32);
+    CKL();
+    if (g.has_in && g.off32) {
+        DevBuf<int32_t> tmp;
+        CK(tmp.ensure((size_t)n));
+        degree_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, g.in_ptr64, tmp.p, g.in_ptr32);
+        CKL();
+        CK(cudaStreamSynchronize(ctx->stream));
+        tmp.release();
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->alloc_slots = 0; // dense state is sized by n
@@ -438,6 +481,8 @@ extern "C" int fora_graph_build_from_edges(fora_ctx* ctx, int32_t n, int64_t m_d
     DevBuf<int32_t> d_src, d_dst, k_src, k_dst;
     DevBuf<unsigned char> keep, tmp;
     DevBuf<int> flags;
+    DevBuf<long long> nsel; // kept-edge counts of the two compactions (64-bit: graphs beyond 2^31 edges use the int64-offset kernels)
+    CK(nsel.ensure(2));
     CK(d_src.ensure(std::max<size_t>(ne, 1))); CK(d_dst.ensure(std::max<size_t>(ne, 1)));
     CK(k_src.ensure(std::max<size_t>(ne, 1))); CK(k_dst.ensure(std::max<size_t>(ne, 1)));
     CK(keep.ensure(std::max<size_t>(ne, 1))); CK(flags.ensure(4));
@@ -449,15 +494,17 @@ extern "C" int fora_graph_build_from_edges(fora_ctx* ctx, int32_t n, int64_t m_d
         k0_flag_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(n_edges, d_src.p, d_dst.p, n, keep.p, flags.p);
         CKL();
         size_t bytes = 0;
-        CK(cub::DeviceSelect::Flagged(nullptr, bytes, d_src.p, keep.p, k_src.p, flags.p + 1, n_edges, ctx->stream));
+        CK(cub::DeviceSelect::Flagged(nullptr, bytes, d_src.p, keep.p, k_src.p, nsel.p, n_edges, ctx->stream));
         CK(tmp.ensure(bytes));
-        CK(cub::DeviceSelect::Flagged(tmp.p, bytes, d_src.p, keep.p, k_src.p, flags.p + 1, n_edges, ctx->stream)); // order preserving
-        CK(cub::DeviceSelect::Flagged(tmp.p, bytes, d_dst.p, keep.p, k_dst.p, flags.p + 2, n_edges, ctx->stream));
+        CK(cub::DeviceSelect::Flagged(tmp.p, bytes, d_src.p, keep.p, k_src.p, nsel.p, n_edges, ctx->stream)); // order preserving
+        CK(cub::DeviceSelect::Flagged(tmp.p, bytes, d_dst.p, keep.p, k_dst.p, nsel.p + 1, n_edges, ctx->stream));
         int hf[4];
+        long long hsel[2];
         CK(cudaMemcpyAsync(hf, flags.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hsel, nsel.p, sizeof(long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         if (hf[0]) return ctx->fail(FORA_ERANGE, "edge list contains a node id >= n (graph.h:155-156)");
-        kept = hf[1];
+        kept = hsel[0];
     }
     free_graph(ctx->g);
     DeviceGraph& g = ctx->g;
@@ -489,7 +536,7 @@ extern "C" int fora_graph_build_from_edges(fora_ctx* ctx, int32_t n, int64_t m_d
         g.has_in = true;
     }
     CK(cudaStreamSynchronize(ctx->stream));
-    d_src.release(); d_dst.release(); k_src.release(); k_dst.release(); keep.release(); tmp.release(); flags.release();
+    d_src.release(); d_dst.release(); k_src.release(); k_dst.release(); keep.release(); tmp.release(); flags.release(); nsel.release();
     ctx->alloc_slots = 0;
     ctx->has_index = false;
     ctx->session_source = -1;
@@ -1363,6 +1410,8 @@ static int ensure_bwd(fora_ctx* ctx) {
     CK(ctx->bwd_rv.ensure(n * nb));
     CK(ctx->bwd_lists.ensure(4 * n * nb));
     CK(cudaMemsetAsync(ctx->bwd_res.p, 0, sizeof(double) * n * nb, ctx->stream));
+    CK(cudaMemsetAsync(ctx->bwd_lists.p, 0, sizeof(int32_t) * 4 * n * nb, ctx->stream)); // stamps start at 0 = never listed
+    ctx->bwd_epoch = 1;
     ctx->bwd_blocks = nb;
     return FORA_OK;
 }
@@ -1372,13 +1421,20 @@ static int launch_bwd(fora_ctx* ctx, int32_t source, double rmax, double omega, 
                       int32_t t_end, double* full_reserve, int keep_residue, u64* d_edges, int32_t* d_overflow) {
     const DeviceGraph& g = ctx->g;
     const int nb = keep_residue ? 1 : std::min(ctx->bwd_blocks, std::max(1, t_end - t_begin));
+    const u32 span = (u32)std::max(1, t_end - t_begin);
+    if (ctx->bwd_epoch > 0xffffffffu - span) { // stamp values would wrap: forget every stamp and start over
+        CK(cudaMemsetAsync(ctx->bwd_lists.p, 0, sizeof(int32_t) * 4 * (size_t)g.n * ctx->bwd_blocks, ctx->stream));
+        ctx->bwd_epoch = 1;
+    }
+    const u32 epoch_base = ctx->bwd_epoch;
+    ctx->bwd_epoch += span;
     if (g.off32) {
         BwdArgs<u32> a{g.n, ctx->p.alpha, rmax, omega, source, g.in_ptr32, g.in_col, g.deg, counts, ctx->bwd_res.p, ctx->bwd_rv.p,
-                       ctx->bwd_lists.p, d_overflow, ppr, t_begin, t_end, full_reserve, keep_residue, d_edges};
+                       ctx->bwd_lists.p, d_overflow, epoch_base, ppr, t_begin, t_end, full_reserve, keep_residue, d_edges};
         bippr_kernel<u32><<<nb, BWD_THREADS, 0, ctx->stream>>>(a);
     } else {
         BwdArgs<int64_t> a{g.n, ctx->p.alpha, rmax, omega, source, g.in_ptr64, g.in_col, g.deg, counts, ctx->bwd_res.p, ctx->bwd_rv.p,
-                           ctx->bwd_lists.p, d_overflow, ppr, t_begin, t_end, full_reserve, keep_residue, d_edges};
+                           ctx->bwd_lists.p, d_overflow, epoch_base, ppr, t_begin, t_end, full_reserve, keep_residue, d_edges};
         bippr_kernel<int64_t><<<nb, BWD_THREADS, 0, ctx->stream>>>(a);
     }
     CKL();
@@ -1412,7 +1468,7 @@ extern "C" int fora_reverse_push(fora_ctx* ctx, int32_t target, double rmax, dou
     int32_t ovf = 0;
     CK(cudaMemcpyAsync(&ovf, ctx->scratch32.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ovf) return ctx->fail(FORA_ECUDA, "backward push: touched list overflow");
+    if (ovf) { ctx->bwd_blocks = 0; return ctx->fail(FORA_ECUDA, "backward push: touched list overflow"); } // scratch is re-zeroed by the next ensure_bwd
     return FORA_OK;
 }
 
@@ -1446,7 +1502,7 @@ static int bippr_one(fora_ctx* ctx, int32_t source, u32 qid, double* d_ppr, u64*
     CK(cudaMemcpyAsync(h2, ctx->scratch64.p, sizeof(u64) * 2, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&ovf, ctx->scratch32.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (ovf) return ctx->fail(FORA_ECUDA, "backward push: touched list overflow");
+    if (ovf) { ctx->bwd_blocks = 0; return ctx->fail(FORA_ECUDA, "backward push: touched list overflow"); }
     *n_walks = nw; *hops = h2[0]; *edges = h2[1];
     return FORA_OK;
 }
@@ -1527,7 +1583,7 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
                 if (h_sources[q0 + s] < 0 || h_sources[q0 + s] >= ctx->g.n) return ctx->fail(FORA_EINVAL, "source out of range");
                 h->source[s] = to_internal(ctx, h_sources[q0 + s]);
             } else h->source[s] = 0;
-            h->qid[s] = (u32)(q0 + s);
+            h->qid[s] = (u32)(ctx->qid_base + (u64)(q0 + s));
         }
         CK(cudaEventRecord(ctx->ev[1], ctx->stream));
         // results leave through a staging buffer on a second stream, so the device->host copy of wave w overlaps the
@@ -1701,7 +1757,7 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
         for (int s = 0; s < cnt; ++s) {
             if (sources[q0 + s] < 0 || sources[q0 + s] >= n) return restore(ctx->fail(FORA_EINVAL, "source out of range"));
             h->source[s] = to_internal(ctx, sources[q0 + s]);
-            h->qid[s] = (u32)(q0 + s);
+            h->qid[s] = (u32)(ctx->qid_base + (u64)(q0 + s));
         }
         const double* result = ctx->reserve.p; // where each slot's final vector lives
         std::vector<int32_t> it(cnt, 0);

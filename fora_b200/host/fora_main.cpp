@@ -308,8 +308,10 @@ static Result do_query(const GraphHost& g, vector<Gpu>& gp) { // query(), query.
     vector<thread> th;
     for (size_t d = 0; d < gp.size(); ++d)
         th.emplace_back([&, d] {
-            if (sh[d].hi > sh[d].lo)
+            if (sh[d].hi > sh[d].lo) {
+                CKF(gp[d].ctx, fora_ctx_set_query_base(gp[d].ctx, (uint64_t)sh[d].lo)); // Philox keyed by the global query index
                 CKF(gp[d].ctx, fora_query_batch(gp[d].ctx, algo_id(), src.data() + sh[d].lo, sh[d].hi - sh[d].lo, nullptr, stats.data() + sh[d].lo, &tms[d]));
+            }
         });
     for (auto& t : th) t.join();
     Result r;
@@ -354,9 +356,11 @@ static Result run_topk(const GraphHost& g, vector<Gpu>& gp, const vector<int32_t
     vector<thread> th;
     for (size_t d = 0; d < gp.size(); ++d)
         th.emplace_back([&, d] {
-            if (sh[d].hi > sh[d].lo)
+            if (sh[d].hi > sh[d].lo) {
+                CKF(gp[d].ctx, fora_ctx_set_query_base(gp[d].ctx, (uint64_t)sh[d].lo)); // Philox keyed by the global query index
                 CKF(gp[d].ctx, fora_topk_batch(gp[d].ctx, algo_id(), src.data() + sh[d].lo, sh[d].hi - sh[d].lo, k, nodes.data() + (size_t)sh[d].lo * k,
                                                values.data() + (size_t)sh[d].lo * k, iters.data() + sh[d].lo, stats.data() + sh[d].lo, &tms[d]));
+            }
         });
     for (auto& t : th) t.join();
     Result r;

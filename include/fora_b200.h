@@ -66,6 +66,11 @@ int fora_ctx_set_stream(fora_ctx* ctx, void* cuda_stream);
 /* number of query slots processed concurrently per launch (dense state = 16*n bytes per slot) */
 int fora_ctx_set_slots(fora_ctx* ctx, int slots);
 int fora_ctx_sync(fora_ctx* ctx);
+/* The Philox streams of a query are keyed by (ctx seed, GLOBAL query index).  The reference processes its query file in one
+ * loop (query.h:1429-1511); a host that shards that list over GPUs, or issues it in several batch calls, passes the list
+ * index of the first query of the next fora_query_batch* / fora_topk_batch call here so that no two queries of a run share a
+ * random stream and results do not depend on how the list was cut.  Sticky; 0 after fora_ctx_create. */
+int fora_ctx_set_query_base(fora_ctx* ctx, uint64_t first_query_index);
 
 /* ------------------------------------------------------------------------------------------
  * Graph  (Graph graph(folder), fora.cpp:176-177 -> graph.h:37-46,89-163)

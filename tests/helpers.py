@@ -337,12 +337,19 @@ class Oracle:
 class Reference:
     """One fresh copy of libfora_ref.so per instance: the reference keeps process-wide globals and
     function-local statics, so every (graph, config) gets its own loaded image."""
+    _in_place_used = False
 
     def __init__(self, g: Graph = None, folder=None, epsilon=0.5, opt=0, balanced=0, with_idx=0, rmax_scale=1.0, k=500):
         assert have_reference(), "oracle/_ref/libfora_ref.so not built (make -C oracle ref)"
-        self._tmp = tempfile.mkdtemp(prefix="fora_ref_so_")
-        so = os.path.join(self._tmp, "libfora_ref.so")
-        shutil.copy(REF_SO, so)
+        # the first instance of a process maps oracle/_ref/libfora_ref.so where it lies (so a loader trace of the process shows the
+        # reference itself); later instances need their own image of the reference's globals and map a private copy
+        if not Reference._in_place_used:
+            Reference._in_place_used = True
+            so = REF_SO
+        else:
+            self._tmp = tempfile.mkdtemp(prefix="fora_ref_so_")
+            so = os.path.join(self._tmp, "libfora_ref.so")
+            shutil.copy(REF_SO, so)
         self.lib = L = C.CDLL(so)
         L.ref_graph_from_csr.argtypes = [C.c_int, C.c_longlong, c_lp, c_ip, c_lp, c_ip]
         L.ref_graph_load_dir.argtypes = [C.c_char_p]
@@ -396,7 +403,8 @@ class Reference:
         assert self.n > 0
 
     def __del__(self):
-        shutil.rmtree(getattr(self, "_tmp", ""), ignore_errors=True)
+        if getattr(self, "_tmp", None):
+            shutil.rmtree(self._tmp, ignore_errors=True)
 
     def graph_dump(self):
         ne = self.lib.ref_graph_num_out_edges()

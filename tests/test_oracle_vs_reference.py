@@ -289,24 +289,29 @@ def test_query_drivers_agree_with_exact(algo):
 
 @pytest.mark.parametrize("opt", [0, 1])
 def test_topk_drivers(opt):
-    # fora_query_topk_new (--opt, query.h:972-1045) / fora_query_topk_with_bound (query.h:909-969)
-    g = Graph.synth(2000, 24000, seed=13)
-    k = 20
+    # fora_query_topk_new (--opt, query.h:972-1045) / fora_query_topk_with_bound (query.h:909-969): average top-k precision
+    # (the reference's compute_precision, algo.h:524-572) of the oracle within 0.01 of the unmodified reference's -- north_star's
+    # tolerance -- over 40 queries at k=200 (8000 ranked entries per arm: the sampling error of the difference is ~0.003)
+    g = Graph.synth(20000, 240000, seed=13)
+    k, nq = 200, 40
     R = Reference(g, epsilon=0.5, opt=opt, k=k)
     O = Oracle(g, seed=3)
     O.set_params(0.5, 0.0, 0.0, opt=opt, k=k)
     R.init_topk_state("fora")
     O.init_state(-9.0, 1)
-    s = 21
-    exact = O.power_iteration(s, 200)
-    top = np.argsort(-exact, kind="stable")[:k]
-    nodes_r, vals_r = R.topk("fora", s, k)
-    if opt:
-        O.fora_topk_new(s)
-    else:
-        O.fora_topk_with_bound(s)
-    nodes_o, vals_o = O.topk_ppr(k)
-    pr = len(set(nodes_r.tolist()) & set(top.tolist())) / k
-    po = len(set(nodes_o.tolist()) & set(top.tolist())) / k
-    assert pr >= 0.8 and po >= 0.8 and abs(pr - po) <= 0.15
-    assert (np.diff(vals_o) <= 0).all() and (np.diff(vals_r) <= 0).all()
+    srcs = np.random.default_rng(5).choice(np.flatnonzero(g.deg > 0), nq, replace=False)
+    pr, po = [], []
+    for s in srcs:
+        s = int(s)
+        exact = O.power_iteration(s, 100)
+        top = np.argsort(-exact, kind="stable")[:k].astype(np.int32)
+        nodes_r, vals_r = R.topk("fora", s, k)
+        if opt:
+            O.fora_topk_new(s)
+        else:
+            O.fora_topk_with_bound(s)
+        nodes_o, vals_o = O.topk_ppr(k)
+        pr.append(R.precision(s, nodes_r, vals_r, top, exact[top])[0])
+        po.append(R.precision(s, nodes_o, vals_o, top, exact[top])[0])
+        assert (np.diff(vals_o) <= 0).all() and (np.diff(vals_r) <= 0).all()
+    assert np.mean(pr) >= 0.9 and np.mean(po) >= 0.9 and abs(np.mean(pr) - np.mean(po)) <= 0.01, (np.mean(pr), np.mean(po))
