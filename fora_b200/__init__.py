@@ -116,6 +116,7 @@ def lib():
     L.fora_random_walks.argtypes = [vp, C.c_int32, C.c_int64, C.c_int, c_ip, c_up]
     L.fora_compute_ppr.argtypes = [vp, c_dp, c_dp, C.c_double, c_dp, C.POINTER(QueryStat)]
     L.fora_query_batch.argtypes = [vp, C.c_int, c_ip, C.c_int32, c_dp, C.POINTER(QueryStat), C.POINTER(BatchTiming)]
+    L.fora_query_batch_sparse.argtypes = [vp, C.c_int, c_ip, C.c_int32, C.c_double, C.c_uint64, C.c_uint64, c_ip, c_dp, c_up, C.POINTER(QueryStat), C.POINTER(BatchTiming)]
     L.fora_query_batch_device.argtypes = [vp, C.c_int, vp, C.c_int32, C.POINTER(QueryStat), C.POINTER(BatchTiming)]
     L.fora_device_ppr.restype = vp
     L.fora_device_ppr.argtypes = [vp, C.c_int]
@@ -131,6 +132,7 @@ def lib():
     L.fora_index_info.argtypes = [vp, c_up, c_up, c_up]
     L.fora_index_build.argtypes = [vp, c_up, c_up, C.c_int32, C.c_int32, c_ip]
     L.fora_index_upload.argtypes = [vp, c_up, c_up, c_ip, C.c_uint64]
+    L.fora_index_build_stat.argtypes = [vp, c_up, c_up, c_dp]
     L.fora_power_iteration.argtypes = [vp, C.c_int32, C.c_int, c_dp]
     _lib = L
     return L
@@ -325,6 +327,19 @@ class Engine:
         self._ck(self.L.fora_query_batch(self.h, ALGO[algo], _p(sources, c_ip), nq, _p(ppr, c_dp), stats, C.byref(tm)))
         return ppr, [stats[i].as_dict() for i in range(nq)], tm.as_dict()
 
+    def query_batch_sparse(self, algo, sources, threshold, cap_per_query, ids=None, vals=None):
+        """compacted result: (ids, vals, offsets) with the entries >= threshold of query i at [offsets[i], offsets[i+1])"""
+        sources = np.ascontiguousarray(sources, np.int32)
+        nq = len(sources)
+        if ids is None:
+            ids, vals = np.empty(nq * cap_per_query, np.int32), np.empty(nq * cap_per_query)
+        off = np.zeros(nq + 1, np.uint64)
+        stats = (QueryStat * max(nq, 1))()
+        tm = BatchTiming()
+        self._ck(self.L.fora_query_batch_sparse(self.h, ALGO[algo], _p(sources, c_ip), nq, threshold, cap_per_query, len(ids), _p(ids, c_ip), _p(vals, c_dp),
+                                                _p(off, c_up), stats, C.byref(tm)))
+        return ids, vals, off, [stats[i].as_dict() for i in range(nq)], tm.as_dict()
+
     def query_batch_device(self, algo, d_sources_ptr, nq):
         stats = (QueryStat * max(nq, 1))()
         tm = BatchTiming()
@@ -382,6 +397,12 @@ class Engine:
         dest = np.empty(hi - lo, np.int32)
         self._ck(self.L.fora_index_build(self.h, _p(off, c_up), _p(cnt, c_up), v_begin, v_end, _p(dest, c_ip)))
         return dest
+
+    def index_build_stat(self):
+        """(walks, hops, walk-kernel ms) of the last index_build call"""
+        w, h, ms = C.c_uint64(0), C.c_uint64(0), C.c_double(0)
+        self._ck(self.L.fora_index_build_stat(self.h, C.byref(w), C.byref(h), C.byref(ms)))
+        return w.value, h.value, ms.value
 
     def index_upload(self, off, cnt, dest):
         off = np.ascontiguousarray(off, np.uint64)

@@ -20,6 +20,7 @@
 #include "bippr.cuh"
 #include "common.cuh"
 #include "push.cuh"
+#include "push2.cuh"
 #include "topk.cuh"
 #include "walk.cuh"
 
@@ -40,6 +41,12 @@ struct SlotMeta {
     u64 nnz[MAX_SLOTS], nsrc[MAX_SLOTS], nwalk[MAX_SLOTS], hops[MAX_SLOTS], idx_hits[MAX_SLOTS];
     double next_rmax[MAX_SLOTS]; // speculative seeding threshold of the following round (0: none)
     u32 seed_count[MAX_SLOTS];   // seeds found for it (segments of front0)
+    // push2 / tail kernels (push2.cuh)
+    u32 force[MAX_SLOTS];        // the tail kernel refused the slot's level for its edge count: the sub-wave kernel runs it
+    u32 left[MAX_SLOTS];         // frontier entries left when the tail kernel returned (0: the slot's round is complete)
+    int32_t push_err;
+    int32_t pad_;
+    u32 sp_count[MAX_SLOTS];     // fora_query_batch_sparse: entries >= threshold found per slot
 };
 
 template <typename T>
@@ -147,6 +154,25 @@ struct fora_ctx {
     DevBuf<int32_t> scratch32;
     DevBuf<double> scratchd;
     int push_grid = 0;
+    // second-generation push (push2.cuh): sub-waves of push_sub slots, tails per slot
+    int push_v = 1, push_sub = 2, push2_grid = 0, push_prefetch = 1;
+    int push_win = 1;          // pin the sub-wave's residue vectors with an access-policy window (persisting L2 lines)
+    int push_win_reset = 0;    // cudaCtxResetPersistingL2Cache after the push phase
+    size_t push_carve = 0;     // persisting carve-out while push2 runs
+    u32 tail_nf = 1024, tail_e = 8192;
+    DevBuf<u32> hubbuf;
+    // bulk walks (index build / Monte-Carlo / BiPPR) through the chunked walk kernel
+    DevBuf<u32> bulk_chunk_first;
+    DevBuf<unsigned char> bulk_meta;
+    DevBuf<u64> bulk_small;
+    // compacted query output (fora_query_batch_sparse)
+    DevBuf<int32_t> sp_ids;
+    DevBuf<double> sp_vals;
+    DevBuf<u32> sp_cnt;
+    cudaEvent_t ev_sp[2] = {};
+    bool sp_busy[2] = {false, false};
+    u64 bulk_walks = 0, bulk_hops = 0;
+    double bulk_kernel_ms = 0;
     // per-kernel timing: event pairs recorded around the hot kernels, harvested after the next stream sync
     std::vector<cudaEvent_t> kev_pool;
     std::vector<std::pair<int, int> > kev_pending; // (pool index of start event, kind 0 push / 1 walk)
@@ -263,7 +289,9 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     free_graph(ctx->g);
     ctx->reserve.release(); ctx->residue.release(); ctx->arena.release(); ctx->front0.release(); ctx->front1.release();
     ctx->log_v.release(); ctx->log_r.release(); ctx->log_cur.release();
-    ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
+    ctx->sp_ids.release(); ctx->sp_vals.release(); ctx->sp_cnt.release();
+    for (auto& e : ctx->ev_sp) if (e) cudaEventDestroy(e);
+    ctx->hubbuf.release(); ctx->bulk_chunk_first.release(); ctx->bulk_meta.release(); ctx->bulk_small.release(); ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
     ctx->ppr.release(); ctx->ub.release(); ctx->lb.release(); ctx->in_topk.release(); ctx->flags.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
@@ -796,6 +824,16 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
                 limit = std::min(ctx->l2_persist_max, b_ptr + ((size_t)1 << 20));
                 if (ctx->win_walk_bytes > limit) { ctx->win_walk_bytes = 0; limit = 0; }
             }
+            ctx->push_v = getenv("FORA_PUSH_V") ? atoi(getenv("FORA_PUSH_V")) : 1; // 2: sub-waves + tails (push2.cuh), still being tuned
+            ctx->push_win = getenv("FORA_PUSH_WIN") ? atoi(getenv("FORA_PUSH_WIN")) : 1;
+            ctx->push_win_reset = getenv("FORA_PUSH_WIN_RESET") ? atoi(getenv("FORA_PUSH_WIN_RESET")) : 0;
+            if (ctx->push_v == 2 && ctx->push_win && ctx->l2_policy && !fits) {
+                // the sub-wave kernel keeps k residue vectors (k x 8n bytes) as persisting lines: without the window the streamed
+                // columns / frontier / log traffic of a level (~2x the vectors' size) evicts them (L2 hit rate 45 %, r2b ncu)
+                ctx->push_carve = getenv("FORA_PUSH_CARVE_MB") ? (size_t)atol(getenv("FORA_PUSH_CARVE_MB")) << 20 : ctx->l2_persist_max;
+                ctx->push_carve = std::min(ctx->push_carve, ctx->l2_persist_max);
+                limit = std::max(limit, ctx->push_carve);
+            }
             if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, limit);
         }
         CK(ctx->front0.ensure(fcap));
@@ -839,6 +877,25 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         }
         if (per_sm < 1) return ctx->fail(FORA_ECUDA, "push kernel does not fit on an SM");
         ctx->push_grid = std::min(per_sm * ctx->num_sms, MAX_PUSH_CTAS);
+        // second-generation push: one 1024-thread CTA per SM for the sub-wave kernel, one CTA per slot for the tails
+        ctx->push_sub = std::max(1, std::min(P2_MAX_SUB, getenv("FORA_PUSH_SUB") ? atoi(getenv("FORA_PUSH_SUB")) : 2));
+        ctx->push_prefetch = getenv("FORA_PUSH_PREFETCH") ? atoi(getenv("FORA_PUSH_PREFETCH")) : 1;
+        ctx->tail_nf = std::min<u32>(TAIL_NF_CAP, getenv("FORA_TAIL_NF") ? (u32)atoi(getenv("FORA_TAIL_NF")) : 1024u);
+        ctx->tail_e = getenv("FORA_TAIL_E") ? (u32)atoi(getenv("FORA_TAIL_E")) : 8192u;
+        CK(ctx->hubbuf.ensure(2 * P2_HUB_CAP + 2));
+        CK(cudaMemsetAsync(ctx->hubbuf.p, 0, sizeof(u32) * (2 * P2_HUB_CAP + 2), ctx->stream));
+        int per_sm2 = 0;
+        if (g.off32) {
+            CK(cudaFuncSetAttribute(push2_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem)));
+            CK(cudaFuncSetAttribute(push_tail_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, push2_kernel<u32>, P2_THREADS, sizeof(P2Smem)));
+        } else {
+            CK(cudaFuncSetAttribute(push2_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P2Smem)));
+            CK(cudaFuncSetAttribute(push_tail_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TailSmem)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, push2_kernel<int64_t>, P2_THREADS, sizeof(P2Smem)));
+        }
+        if (per_sm2 < 1) return ctx->fail(FORA_ECUDA, "push2 kernel does not fit on an SM");
+        ctx->push2_grid = ctx->num_sms; // one CTA per SM: the grid barrier has 148 participants
     }
     // walks per slot <= omega*rsum + #sources <= omega + n
     const size_t need = std::max((size_t)WALK_TARGET_CHUNKS + 1, (size_t)((omega_max + (double)n) / WALK_CHUNK)) + 4; // see walk_chunk_size
@@ -850,7 +907,7 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
 }
 
 // Pin [arena+off, +bytes) in L2 for the kernels launched next on the work stream (bytes == 0 clears).
-static int set_l2_window(fora_ctx* ctx, size_t off, size_t bytes) {
+static int set_l2_window(fora_ctx* ctx, size_t off, size_t bytes, size_t carve = 0) {
     if (!ctx->l2_policy || bytes == 0) return FORA_OK;
     cudaStreamAttrValue av;
     memset(&av, 0, sizeof av);
@@ -858,7 +915,7 @@ static int set_l2_window(fora_ctx* ctx, size_t off, size_t bytes) {
         const size_t wb = std::min(bytes, ctx->l2_window_max);
         av.accessPolicyWindow.base_ptr = ctx->arena.p + off;
         av.accessPolicyWindow.num_bytes = wb;
-        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)ctx->l2_persist_max / (double)wb);
+        av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)(carve ? carve : ctx->l2_persist_max) / (double)wb);
         av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
         av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
     } else {
@@ -891,6 +948,7 @@ static void kev_harvest(fora_ctx* ctx) {
         float ms = 0;
         if (cudaEventElapsedTime(&ms, ctx->kev_pool[pr.first], ctx->kev_pool[pr.first + 1]) == cudaSuccess) {
             if (pr.second == 0) { ctx->push_kernel_ms += ms; ctx->push_kernel_launches++; }
+            else if (pr.second == 2) ctx->push_kernel_ms += ms; // further kernels of the same push round
             else { ctx->walk_kernel_ms += ms; ctx->walk_kernel_launches++; }
         }
     }
@@ -967,7 +1025,9 @@ static int apply_push_log(fora_ctx* ctx) {
 
 // launch the persistent push kernel over whatever frontier is in front0 / ctl->fcount[0].  defer_log: leave the reserve
 // credits of this launch in the log (the caller applies them once after the last round of the wave).
+static int launch_push2(fora_ctx* ctx, bool defer_log);
 static int launch_push(fora_ctx* ctx, bool defer_log = false) {
+    if (ctx->push_v == 2) return launch_push2(ctx, defer_log);
     PushArgs a = make_push_args(ctx);
     ctx->level_base += (1u << 20);
     int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
@@ -987,14 +1047,84 @@ static int launch_push(fora_ctx* ctx, bool defer_log = false) {
     return defer_log ? FORA_OK : apply_push_log(ctx);
 }
 
+// Second-generation push of one round over whatever frontier is installed (push2.cuh): the tail kernel runs the small levels of
+// every slot concurrently (one CTA per slot), the sub-wave kernel runs the large levels of push_sub slots at a time with their
+// residue vectors L2-resident; repeat until every frontier is empty (normally: head -> sub-waves -> tail, one pass).
+static int launch_push2(fora_ctx* ctx, bool defer_log) {
+    Push2Args a{};
+    a.p = make_push_args(ctx);
+    SlotMeta* m = ctx->meta.p;
+    a.tail_nf = ctx->tail_nf;
+    a.tail_e = ctx->tail_e;
+    a.rv = ctx->inc.p;
+    a.hub = ctx->hubbuf.p;
+    a.hub_cnt = ctx->hubbuf.p + 2 * P2_HUB_CAP;
+    a.force = m->force;
+    a.left = m->left;
+    a.err = &m->push_err;
+    a.prefetch = ctx->push_prefetch;
+    const int S = ctx->slots, K = ctx->push_sub;
+    int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
+    if (wrc) return wrc;
+    auto tail = [&]() -> int {
+        a.slot0 = 0;
+        a.k = S;
+        if (ctx->g.off32) {
+            CsrView<u32> v{ctx->hot_ptr32, ctx->g.out_col};
+            push_tail_kernel<u32><<<S, TAIL_THREADS, sizeof(TailSmem), ctx->stream>>>(a, v);
+        } else {
+            CsrView<int64_t> v{ctx->g.out_ptr64, ctx->g.out_col};
+            push_tail_kernel<int64_t><<<S, TAIL_THREADS, sizeof(TailSmem), ctx->stream>>>(a, v);
+        }
+        CKL();
+        return FORA_OK;
+    };
+    int rc;
+    kev_begin(ctx, 0);
+    if ((rc = tail())) return rc;
+    kev_end(ctx);
+    for (int rep = 0;; ++rep) {
+        if ((rc = meta_d2h_sync(ctx))) return rc; // which slots still hold a frontier (mapped memory, no copy engine)
+        if (ctx->h_meta->push_err) return ctx->fail(FORA_ECUDA, "push: level cap reached");
+        bool any = false;
+        for (int s = 0; s < S; ++s) any = any || ctx->h_meta->left[s] != 0;
+        if (!any) break;
+        if (rep >= 4096) return ctx->fail(FORA_ECUDA, "push: the frontier does not drain");
+        kev_begin(ctx, 2);
+        for (int s0 = 0; s0 < S; s0 += K) {
+            const int k = std::min(K, S - s0);
+            bool need = false;
+            for (int s = s0; s < s0 + k; ++s) need = need || ctx->h_meta->left[s] != 0;
+            if (!need) continue;
+            a.slot0 = s0;
+            a.k = k;
+            if (ctx->push_carve) { // this sub-wave's residue vectors become the persisting part of the L2
+                int w2 = set_l2_window(ctx, (size_t)((unsigned char*)(ctx->residue.p + (size_t)s0 * ctx->g.n) - ctx->arena.p), sizeof(double) * (size_t)k * ctx->g.n, ctx->push_carve);
+                if (w2) return w2;
+            }
+            if (ctx->g.off32) {
+                CsrView<u32> v{ctx->hot_ptr32, ctx->g.out_col};
+                void* args[] = {&a, &v};
+                CK(cudaLaunchCooperativeKernel((void*)push2_kernel<u32>, dim3(ctx->push2_grid), dim3(P2_THREADS), args, sizeof(P2Smem), ctx->stream));
+            } else {
+                CsrView<int64_t> v{ctx->g.out_ptr64, ctx->g.out_col};
+                void* args[] = {&a, &v};
+                CK(cudaLaunchCooperativeKernel((void*)push2_kernel<int64_t>, dim3(ctx->push2_grid), dim3(P2_THREADS), args, sizeof(P2Smem), ctx->stream));
+            }
+            ctx->launches++;
+        }
+        if ((rc = tail())) return rc;
+        kev_end(ctx);
+    }
+    if (ctx->push_carve && ctx->push_win_reset) cudaCtxResetPersistingL2Cache();
+    return defer_log ? FORA_OK : apply_push_log(ctx);
+}
+
 // rsum / nnz of every slot; with seed_next also the seed lists of the next round at h_meta->next_rmax
 static int launch_residue_stats(fora_ctx* ctx, bool seed_next = false) {
     const int S = ctx->slots;
     SlotMeta* m = ctx->meta.p;
-    if (seed_next) {
-        CK(cudaMemcpyAsync(m->next_rmax, ctx->h_meta->next_rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(m->seed_count, 0, sizeof(u32) * MAX_SLOTS, ctx->stream));
-    }
+    if (seed_next) CK(cudaMemsetAsync(m->seed_count, 0, sizeof(u32) * MAX_SLOTS, ctx->stream)); // next_rmax was uploaded by push_round_active
     residue_partial_kernel<<<dim3(ctx->red_blocks, S), RED_THREADS, 0, ctx->stream>>>(ctx->g.n, ctx->residue.p, ctx->part_sum.p, ctx->part_nnz.p, ctx->hot_deg,
                                                                                      seed_next ? m->next_rmax : nullptr, ctx->front0.p, m->seed_count);
     CKL();
@@ -1012,7 +1142,9 @@ static int init_wave(fora_ctx* ctx, int cnt, int seed_source, const int32_t* d_s
         h->state[s] = 0; h->active[s] = 0; h->edges[s] = h->vertices[s] = h->levels[s] = 0;
         h->lastlvl[s] = 0; h->rsum[s] = 0; h->nnz[s] = h->nsrc[s] = h->nwalk[s] = h->hops[s] = h->idx_hits[s] = 0;
         h->rmax[s] = ctx->p.rmax;
+        h->force[s] = h->left[s] = 0;
     }
+    h->push_err = 0;
     ctx->level_base = 0;
     int rc = meta_h2d(ctx);
     if (rc) return rc;
@@ -1039,6 +1171,8 @@ static int push_round_active(fora_ctx* ctx, bool have_seeds = false, bool next_s
     SlotMeta* h = ctx->h_meta;
     CK(cudaMemcpyAsync(ctx->meta.p->rmax, h->rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->meta.p->active, h->active, sizeof(int32_t) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+    // before the push: launch_push2 mirrors the device block back into h_meta while it drains the frontier
+    if (next_seed) CK(cudaMemcpyAsync(ctx->meta.p->next_rmax, h->next_rmax, sizeof(double) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->ctl.p, 0, sizeof(PushCtl), ctx->stream));
     if (have_seeds) {
         u32 cnt[MAX_SLOTS];
@@ -1330,20 +1464,103 @@ extern "C" int fora_push_round(fora_ctx* ctx, double rmax, double* reserve, doub
 // =============================================================================================
 // walks test hook / Monte-Carlo building block
 // =============================================================================================
-static int launch_bulk(fora_ctx* ctx, const BulkArgs& ba, int no_zero_hop) {
+// Bulk walks -- index build (build.h:344-354), montecarlo_query / bippr_query (query.h:25-31, 81-88), the random_walk test
+// hook -- run through the SAME chunked, warp-converged walk kernel as the query path (walk.cuh), with the destination stored
+// at the walk's global index (OUT_DEST) or counted (OUT_COUNT) instead of added to a PPR vector.  The plan is the query
+// path's: sources (internal ids) with an exclusive prefix of their walk counts.
+struct BulkPlan {
+    const int32_t* d_srcs = nullptr; // [nsrc] internal vertex ids, every one with at least one walk
+    const u64* d_woff = nullptr;     // [nsrc + 1]
+    u64 nsrc = 0, nwalk = 0;
+    int32_t* out_dest = nullptr;     // device [nwalk], original ids (OUT_DEST) ...
+    u64* out_counts = nullptr;       // ... or device [n] histogram in internal ids (OUT_COUNT)
+    u32 key_tag = 0;                 // distinguishes index build / MC / BiPPR / test streams
+    int no_zero_hop = 0;
+};
+struct BulkMeta { // what walk_kernel reads per slot; slot 0 of a private block
+    u64 nsrc, nwalk, hops, idx_hits;
+    int32_t state;
+    u32 qid;
+};
+// parts > 1: one launch per contiguous chunk range, after_part(part, first walk, end walk) behind each (e.g. to ship that slice)
+static int launch_bulk(fora_ctx* ctx, const BulkPlan& bp, u64* hops_out, int parts = 1,
+                       const std::function<int(int, u64, u64)>& after_part = nullptr) {
     const DeviceGraph& g = ctx->g;
-    const int gx = (int)std::max<u64>(1, std::min<u64>((u64)ctx->num_sms * 8, (ba.total + WALK_THREADS - 1) / WALK_THREADS));
-    if (g.off32) {
-        CsrView<u32> v{g.out_ptr32, g.out_col};
-        if (no_zero_hop) bulk_walk_kernel<u32, true><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
-        else bulk_walk_kernel<u32, false><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
-    } else {
-        CsrView<int64_t> v{g.out_ptr64, g.out_col};
-        if (no_zero_hop) bulk_walk_kernel<int64_t, true><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
-        else bulk_walk_kernel<int64_t, false><<<gx, WALK_THREADS, 0, ctx->stream>>>(ba, v);
-    }
+    if (hops_out) *hops_out = 0;
+    if (bp.nwalk == 0) return FORA_OK;
+    const u64 CH = walk_chunk_size(bp.nwalk);
+    const u64 nchunks = (bp.nwalk + CH - 1) / CH;
+    CK(ctx->bulk_chunk_first.ensure(nchunks + 2));
+    CK(ctx->bulk_meta.ensure(sizeof(BulkMeta)));
+    BulkMeta hm{};
+    hm.nsrc = bp.nsrc; hm.nwalk = bp.nwalk; hm.state = 1; hm.qid = bp.key_tag;
+    CK(cudaMemcpyAsync(ctx->bulk_meta.p, &hm, sizeof hm, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // hm lives on this stack frame
+    BulkMeta* dm = (BulkMeta*)ctx->bulk_meta.p;
+    const int cgx = (int)std::max<u64>(1, std::min<u64>((u64)ctx->num_sms * 4, (nchunks + 256) / 256));
+    chunk_start_kernel<<<dim3(cgx, 1), 256, 0, ctx->stream>>>(g.n, bp.d_woff, &dm->nsrc, &dm->nwalk, ctx->bulk_chunk_first.p, (size_t)(nchunks + 2), &dm->state);
     CKL();
+    WalkArgs wa{};
+    wa.n = g.n;
+    wa.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
+    wa.seed_lo = (u32)ctx->seed; wa.seed_hi = (u32)(ctx->seed >> 32);
+    wa.srcs = bp.d_srcs; wa.woff = bp.d_woff; wa.incs = nullptr; wa.nsrc = &dm->nsrc; wa.nwalk = &dm->nwalk;
+    wa.chunk_first = ctx->bulk_chunk_first.p; wa.chunk_cap = (size_t)(nchunks + 2); wa.slot_state = &dm->state; wa.qid = &dm->qid;
+    wa.round_tag = 0x5bd1e995u; wa.hops = &dm->hops; wa.idx_hits = &dm->idx_hits;
+    wa.out_dest = bp.out_dest; wa.out_counts = bp.out_counts; wa.new2old = g.relabeled ? g.new2old : nullptr;
+    parts = (int)std::max<u64>(1, std::min<u64>((u64)parts, nchunks));
+    wa.nparts = (u32)parts;
+    const bool to_dest = bp.out_dest != nullptr;
+    for (int part = 0; part < parts; ++part) {
+        wa.part = (u32)part;
+        const u64 c_lo = parts > 1 ? nchunks * (u64)part / (u64)parts : 0, c_hi = parts > 1 ? nchunks * (u64)(part + 1) / (u64)parts : nchunks;
+        const dim3 grid((unsigned)std::max<u64>(1, std::min<u64>((u64)ctx->num_sms * 16, c_hi - c_lo)), 1);
+        kev_begin(ctx, 1);
+        if (g.off32) {
+            CsrView<u32> v{g.out_ptr32, g.out_col};
+            if (to_dest) {
+                if (bp.no_zero_hop) walk_kernel<u32, true, false, OUT_DEST><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+                else walk_kernel<u32, false, false, OUT_DEST><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            } else {
+                if (bp.no_zero_hop) walk_kernel<u32, true, false, OUT_COUNT><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+                else walk_kernel<u32, false, false, OUT_COUNT><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            }
+        } else {
+            CsrView<int64_t> v{g.out_ptr64, g.out_col};
+            if (to_dest) {
+                if (bp.no_zero_hop) walk_kernel<int64_t, true, false, OUT_DEST><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+                else walk_kernel<int64_t, false, false, OUT_DEST><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            } else {
+                if (bp.no_zero_hop) walk_kernel<int64_t, true, false, OUT_COUNT><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+                else walk_kernel<int64_t, false, false, OUT_COUNT><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            }
+        }
+        kev_end(ctx);
+        CKL();
+        if (after_part) {
+            int arc = after_part(part, c_lo * CH, std::min(bp.nwalk, c_hi * CH));
+            if (arc) return arc;
+        }
+    }
+    if (hops_out) {
+        CK(cudaMemcpyAsync(hops_out, &dm->hops, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        kev_harvest(ctx);
+    }
     return FORA_OK;
+}
+// `count` walks from ONE source (internal id): the plan is a single segment
+static int launch_bulk_single(fora_ctx* ctx, int32_t source_internal, u64 count, int32_t* out_dest, u64* out_counts, u32 key_tag, int no_zero_hop,
+                              u64* hops_out) {
+    CK(ctx->bulk_small.ensure(4));
+    const u64 hw[4] = {0, count, (u64)(u32)source_internal, 0};
+    CK(cudaMemcpyAsync(ctx->bulk_small.p, hw, sizeof hw, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    BulkPlan bp;
+    bp.d_srcs = (const int32_t*)(ctx->bulk_small.p + 2); // low word of the third entry (little endian)
+    bp.d_woff = ctx->bulk_small.p;
+    bp.nsrc = 1; bp.nwalk = count; bp.out_dest = out_dest; bp.out_counts = out_counts; bp.key_tag = key_tag; bp.no_zero_hop = no_zero_hop;
+    return launch_bulk(ctx, bp, hops_out);
 }
 
 extern "C" int fora_random_walks(fora_ctx* ctx, int32_t start, int64_t count, int no_zero_hop, int32_t* dest, uint64_t* hops) {
@@ -1351,18 +1568,11 @@ extern "C" int fora_random_walks(fora_ctx* ctx, int32_t start, int64_t count, in
     if (start < 0 || start >= ctx->g.n || count < 0) return ctx->fail(FORA_EINVAL, "bad start/count");
     CK(cudaSetDevice(ctx->device));
     CK(ctx->scratch32.ensure((size_t)std::max<int64_t>(count, 1)));
-    CK(ctx->scratch64.ensure(1));
-    CK(cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(u64), ctx->stream));
-    BulkArgs ba{};
-    ba.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
-    ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
-    ba.key_tag = 0x77a1c5u;
-    ba.single = start; ba.total = (u64)count; ba.dest = ctx->scratch32.p; ba.counts = nullptr; ba.hops = ctx->scratch64.p;
-    ba.old2new = ctx->g.relabeled ? ctx->g.old2new : nullptr; ba.new2old = ctx->g.relabeled ? ctx->g.new2old : nullptr;
-    int rc = launch_bulk(ctx, ba, no_zero_hop);
+    u64 h = 0;
+    int rc = launch_bulk_single(ctx, to_internal(ctx, start), (u64)count, ctx->scratch32.p, nullptr, 0x77a1c5u, no_zero_hop, &h);
     if (rc) return rc;
-    if (dest) CK(cudaMemcpyAsync(dest, ctx->scratch32.p, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
-    if (hops) CK(cudaMemcpyAsync(hops, ctx->scratch64.p, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+    if (dest && count) CK(cudaMemcpyAsync(dest, ctx->scratch32.p, sizeof(int32_t) * (size_t)count, cudaMemcpyDeviceToHost, ctx->stream));
+    if (hops) *hops = h;
     CK(cudaStreamSynchronize(ctx->stream));
     return FORA_OK;
 }
@@ -1484,12 +1694,8 @@ static int bippr_one(fora_ctx* ctx, int32_t source, u32 qid, double* d_ppr, u64*
     CK(cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(u64) * 4, ctx->stream));
     CK(cudaMemsetAsync(ctx->scratch32.p, 0, sizeof(int32_t) * 4, ctx->stream));
     const u64 nw = (u64)ceil(p.omega); // for(i=0; i<omega; i++), query.h:81
-    BulkArgs ba{};
-    ba.alpha_thr = (u32)std::min(4294967295.0, p.alpha * 4294967296.0);
-    ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
-    ba.key_tag = 0x42500000u + qid;
-    ba.single = source; ba.total = nw; ba.dest = nullptr; ba.counts = ctx->counts.p; ba.hops = ctx->scratch64.p;
-    if ((rc = launch_bulk(ctx, ba, 0))) return rc;
+    u64 walk_hops = 0;
+    if ((rc = launch_bulk_single(ctx, source, nw, nullptr, ctx->counts.p, 0x42500000u + qid, 0, &walk_hops))) return rc;
     if (p.rmax < 1.0) { // query.h:91
         if ((rc = ensure_bwd(ctx))) return rc;
         if ((rc = launch_bwd(ctx, source, p.rmax, p.omega, ctx->counts.p, d_ppr, 0, ctx->g.n, nullptr, 0, ctx->scratch64.p + 1, ctx->scratch32.p))) return rc;
@@ -1503,7 +1709,7 @@ static int bippr_one(fora_ctx* ctx, int32_t source, u32 qid, double* d_ppr, u64*
     CK(cudaMemcpyAsync(&ovf, ctx->scratch32.p, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ovf) { ctx->bwd_blocks = 0; return ctx->fail(FORA_ECUDA, "backward push: touched list overflow"); }
-    *n_walks = nw; *hops = h2[0]; *edges = h2[1];
+    *n_walks = nw; *hops = walk_hops; *edges = h2[1];
     return FORA_OK;
 }
 
@@ -1557,8 +1763,50 @@ extern "C" int fora_compute_ppr_part_device(fora_ctx* ctx, double rsum, uint32_t
 // =============================================================================================
 // queries
 // =============================================================================================
+// Compacted result: (original id, value) of every entry >= threshold of the dense vectors of slots [slot_lo, slot_lo + gridDim.y),
+// appended per slot (unordered).  A block counts first and reserves its places with one atomic.
+__global__ void __launch_bounds__(256) sparse_out_kernel(int32_t n, const double* __restrict__ ppr, const int32_t* __restrict__ new2old, double thr,
+                                                         u32 cap, int slot_lo, int32_t* __restrict__ ids, double* __restrict__ vals, u32* __restrict__ cnt) {
+    __shared__ u32 s_cnt[8];
+    __shared__ u32 s_base;
+    const int slot = slot_lo + (int)blockIdx.y;
+    const double* __restrict__ v = ppr + (size_t)slot * n;
+    const int per_block = (n + gridDim.x - 1) / gridDim.x;
+    const int lo = min(n, (int)blockIdx.x * per_block), hi = min(n, lo + per_block);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    u32 mine = 0;
+    for (int i = lo + (int)threadIdx.x; i < hi; i += 256) mine += v[i] >= thr;
+    const u32 wi = warp_incl_scan(mine);
+    if (lane == 31) s_cnt[w] = wi;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 acc = 0;
+        for (int t = 0; t < 8; ++t) { const u32 x = s_cnt[t]; s_cnt[t] = acc; acc += x; }
+        s_base = acc ? atomicAdd(&cnt[slot], acc) : 0u;
+    }
+    __syncthreads();
+    u32 pos = s_base + s_cnt[w] + wi - mine;
+    for (int i = lo + (int)threadIdx.x; i < hi; i += 256) {
+        const double x = v[i];
+        if (x >= thr) {
+            if (pos < cap) {
+                ids[(size_t)slot * cap + pos] = new2old ? new2old[i] : i;
+                vals[(size_t)slot * cap + pos] = x;
+            }
+            ++pos;
+        }
+    }
+}
+struct SparseOut { // fora_query_batch_sparse
+    double threshold;
+    u64 cap_per_query, cap_total;
+    int32_t* ids;
+    double* vals;
+    uint64_t* offsets; // [n_q + 1]
+};
+
 static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, const int32_t* d_sources, int32_t n_q, double* ppr,
-                            fora_query_stat* stats, fora_batch_timing* timing) {
+                            fora_query_stat* stats, fora_batch_timing* timing, const SparseOut* sp = nullptr) {
     int rc = require_ready(ctx, ctx ? ctx->p.omega : 0);
     if (rc) return rc;
     if (n_q < 0 || (!h_sources && !d_sources && n_q)) return ctx->fail(FORA_EINVAL, "bad sources");
@@ -1576,6 +1824,19 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
     std::vector<double> fr(S);
     std::vector<u64> rounds(S);
     SlotMeta* h = ctx->h_meta;
+    u32 sp_cap = 0;
+    u64 sp_total = 0;
+    int sp_wave = 0;
+    if (sp) { // compacted output: two device buffers (wave parity) so that the copy of wave w runs under wave w+1
+        if (!sp->ids || !sp->vals || !sp->offsets || !(sp->threshold > 0.0)) return ctx->fail(FORA_EINVAL, "sparse output: ids / vals / offsets and a positive threshold are required");
+        sp_cap = (u32)std::min<u64>({sp->cap_per_query, (u64)n, (u64)0xfffffff0u});
+        if (sp_cap == 0) return ctx->fail(FORA_EINVAL, "sparse output: cap_per_query is 0");
+        CK(ctx->sp_ids.ensure((size_t)2 * S * sp_cap));
+        CK(ctx->sp_vals.ensure((size_t)2 * S * sp_cap));
+        CK(ctx->sp_cnt.ensure((size_t)2 * MAX_SLOTS));
+        sp->offsets[0] = 0;
+        for (auto& e : ctx->ev_sp) if (!e) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     for (int32_t q0 = 0; q0 < n_q; q0 += S) {
         const int cnt = std::min<int32_t>(S, n_q - q0);
         for (int s = 0; s < cnt; ++s) {
@@ -1637,26 +1898,36 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
             const u64 nw = (u64)ceil(ctx->p.omega); // for(i=0; i<omega; i++), query.h:25
             for (int s = 0; s < cnt; ++s) {
                 CK(cudaMemsetAsync(ctx->counts.p, 0, sizeof(u64) * n, ctx->stream));
-                BulkArgs ba{};
-                ba.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
-                ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
-                ba.key_tag = 0x4d430000u + h->qid[s];
-                ba.single = h->source[s]; ba.total = nw; ba.dest = nullptr; ba.counts = ctx->counts.p;
-                ba.hops = &ctx->meta.p->hops[s];
+                int32_t src_int = h->source[s];
                 if (d_sources) { // source id lives on the device: fetch it (tiny)
                     int32_t sv;
                     CK(cudaMemcpyAsync(&sv, d_sources + q0 + s, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
                     CK(cudaStreamSynchronize(ctx->stream));
-                    ba.single = to_internal(ctx, sv);
+                    src_int = to_internal(ctx, sv);
                 }
-                if ((rc = launch_bulk(ctx, ba, 0))) return rc;
+                u64 hp = 0;
+                if ((rc = launch_bulk_single(ctx, src_int, nw, nullptr, ctx->counts.p, 0x4d430000u + h->qid[s], 0, &hp))) return rc;
+                h->hops[s] = hp;
                 counts_to_ppr_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->g.n, ctx->counts.p, ctx->p.omega, ctx->reserve.p + n * s);
                 CKL();
                 h->nwalk[s] = nw;
             }
             CK(cudaMemcpyAsync(ctx->meta.p->nwalk, h->nwalk, sizeof(u64) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(ctx->meta.p->hops, h->hops, sizeof(u64) * MAX_SLOTS, cudaMemcpyHostToDevice, ctx->stream));
         }
         CK(cudaEventRecord(ctx->ev[3], ctx->stream));
+        u32* sp_cnt_dev = nullptr;
+        if (sp) { // compaction on the work stream; counts reach the host with the wave's control block below
+            const int b = sp_wave & 1;
+            if (ctx->sp_busy[b]) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_sp[b], 0)); // the copy of wave w-2 has left this buffer
+            sp_cnt_dev = ctx->sp_cnt.p + (size_t)b * MAX_SLOTS;
+            CK(cudaMemsetAsync(sp_cnt_dev, 0, sizeof(u32) * MAX_SLOTS, ctx->stream));
+            const int gx = std::max(1, std::min(ctx->num_sms * 8 / std::max(cnt, 1) + 1, (int)((n + 2047) / 2048)));
+            sparse_out_kernel<<<dim3(gx, cnt), 256, 0, ctx->stream>>>(ctx->g.n, ctx->reserve.p, ctx->g.relabeled ? ctx->g.new2old : nullptr, sp->threshold, sp_cap, 0,
+                                                                   ctx->sp_ids.p + (size_t)b * S * sp_cap, ctx->sp_vals.p + (size_t)b * S * sp_cap, sp_cnt_dev);
+            CKL();
+            CK(cudaMemcpyAsync(ctx->meta.p->sp_count, sp_cnt_dev, sizeof(u32) * MAX_SLOTS, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
         if (ppr && !shipped) {
             CK(ctx->stage.ensure(n * (size_t)S));
             if (ctx->stage_busy) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
@@ -1664,6 +1935,23 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
         }
         CK(cudaEventRecord(ctx->ev[4], ctx->stream));
         if ((rc = meta_d2h_sync(ctx))) return rc;
+        if (sp) { // the wave has finished (sync above): ship exactly the entries found, on the copy stream, under the next wave
+            const int b = sp_wave & 1;
+            for (int s = 0; s < cnt; ++s) {
+                const u64 c = h->sp_count[s];
+                if (c > sp_cap) return ctx->fail(FORA_ERANGE, "sparse output: a query has more entries >= threshold than cap_per_query");
+                if (sp_total + c > sp->cap_total) return ctx->fail(FORA_ERANGE, "sparse output: cap_total exceeded");
+                if (c) {
+                    CK(cudaMemcpyAsync(sp->ids + sp_total, ctx->sp_ids.p + ((size_t)b * S + s) * sp_cap, sizeof(int32_t) * c, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                    CK(cudaMemcpyAsync(sp->vals + sp_total, ctx->sp_vals.p + ((size_t)b * S + s) * sp_cap, sizeof(double) * c, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                }
+                sp_total += c;
+                sp->offsets[q0 + s + 1] = sp_total;
+            }
+            CK(cudaEventRecord(ctx->ev_sp[b], ctx->copy_stream));
+            ctx->sp_busy[b] = true;
+            ++sp_wave;
+        }
         if (stats)
             for (int s = 0; s < cnt; ++s) fill_stat(ctx, s, algo == FORA_ALGO_FORA ? fr[s] : ctx->p.rmax, algo == FORA_ALGO_MC ? 0 : rounds[s], &stats[q0 + s]);
         float t;
@@ -1675,6 +1963,11 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_stage_free, 0));
         ctx->stage_busy = false;
     }
+    for (int b = 0; b < 2; ++b)
+        if (ctx->sp_busy[b]) {
+            CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_sp[b], 0));
+            ctx->sp_busy[b] = false;
+        }
     CK(cudaEventRecord(ctx->ev[5], ctx->stream));
     CK(cudaEventSynchronize(ctx->ev[5]));
     if (timing) {
@@ -1691,6 +1984,13 @@ static int query_batch_impl(fora_ctx* ctx, int algo, const int32_t* h_sources, c
 extern "C" int fora_query_batch(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, double* ppr,
                                 fora_query_stat* stats, fora_batch_timing* timing) {
     return query_batch_impl(ctx, algo, sources, nullptr, n_q, ppr, stats, timing);
+}
+extern "C" int fora_query_batch_sparse(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, double threshold, uint64_t cap_per_query,
+                                       uint64_t cap_total, int32_t* ids, double* values, uint64_t* offsets, fora_query_stat* stats,
+                                       fora_batch_timing* timing) {
+    if (!ctx) return FORA_EINVAL;
+    SparseOut sp{threshold, cap_per_query, cap_total, ids, values, offsets};
+    return query_batch_impl(ctx, algo, sources, nullptr, n_q, nullptr, stats, timing, &sp);
 }
 extern "C" int fora_query_batch_device(fora_ctx* ctx, int algo, const int32_t* d_sources, int32_t n_q, fora_query_stat* stats,
                                        fora_batch_timing* timing) {
@@ -2030,28 +2330,62 @@ extern "C" int fora_index_build(fora_ctx* ctx, const uint64_t* offsets, const ui
     if (!offsets || !counts || !dest || v_begin < 0 || v_end > ctx->g.n || v_begin > v_end) return ctx->fail(FORA_EINVAL, "bad range");
     CK(cudaSetDevice(ctx->device));
     const u64 nseg = (u64)(v_end - v_begin);
+    ctx->bulk_walks = ctx->bulk_hops = 0;
+    ctx->bulk_kernel_ms = 0;
     if (nseg == 0) return FORA_OK;
     const u64 base = offsets[v_begin];
     const u64 total = offsets[v_end - 1] + counts[v_end - 1] - base;
     if (total == 0) return FORA_OK;
-    std::vector<u64> rel(nseg + 1);
-    for (u64 i = 0; i < nseg; ++i) rel[i] = offsets[v_begin + i] - base;
-    rel[nseg] = total;
-    CK(ctx->scratch64.ensure(nseg + 2));
-    CK(ctx->scratch32.ensure(total));
-    CK(cudaMemcpyAsync(ctx->scratch64.p + 1, rel.data(), sizeof(u64) * (nseg + 1), cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(u64), ctx->stream));
-    BulkArgs ba{};
-    ba.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
-    ba.seed_lo = (u32)ctx->seed; ba.seed_hi = (u32)(ctx->seed >> 32);
-    ba.key_tag = 0x1d800000u;
-    ba.seg_off = ctx->scratch64.p + 1; ba.v_begin = v_begin; ba.single = -1; ba.nseg = nseg; ba.total = total;
-    ba.dest = ctx->scratch32.p; ba.counts = nullptr; ba.hops = ctx->scratch64.p;
-    ba.old2new = ctx->g.relabeled ? ctx->g.old2new : nullptr; ba.new2old = ctx->g.relabeled ? ctx->g.new2old : nullptr;
-    int rc = launch_bulk(ctx, ba, ctx->p.opt); // build.h:347-350
+    // the walk plan of the query path: sources with at least one walk (internal ids, in ORIGINAL vertex order = index order)
+    // and the exclusive prefix of their counts, which is the index offset relative to this source range (build.h:337-352)
+    std::vector<int32_t> srcs;
+    std::vector<u64> woff;
+    srcs.reserve(nseg);
+    woff.reserve(nseg + 1);
+    for (u64 i = 0; i < nseg; ++i) {
+        if (counts[v_begin + i] == 0) continue;
+        if (offsets[v_begin + i] - base + counts[v_begin + i] > total) return ctx->fail(FORA_EINVAL, "index info is not an exclusive prefix of the counts");
+        srcs.push_back(to_internal(ctx, (int32_t)(v_begin + (int64_t)i)));
+        woff.push_back(offsets[v_begin + i] - base);
+    }
+    woff.push_back(total);
+    const u64 ns = srcs.size();
+    CK(ctx->scratch64.ensure(ns + 1));
+    CK(ctx->scratch32.ensure(total + ns));
+    int32_t* d_srcs = ctx->scratch32.p + total;
+    CK(cudaMemcpyAsync(ctx->scratch64.p, woff.data(), sizeof(u64) * (ns + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d_srcs, srcs.data(), sizeof(int32_t) * ns, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream)); // the host vectors go out of scope below
+    BulkPlan bp;
+    bp.d_srcs = d_srcs; bp.d_woff = ctx->scratch64.p; bp.nsrc = ns; bp.nwalk = total; bp.out_dest = ctx->scratch32.p;
+    bp.key_tag = 0x1d800000u; bp.no_zero_hop = ctx->p.opt; // build.h:347-350
+    // destinations leave in slices while the remaining walks still run: slice p is copied on the copy stream behind launch p
+    const int parts = (int)std::max<u64>(1, std::min<u64>(16, total / (8u << 20)));
+    std::vector<cudaEvent_t> evs((size_t)parts);
+    for (auto& e : evs) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const double ms0 = ctx->walk_kernel_ms;
+    u64 hops = 0;
+    int rc = launch_bulk(ctx, bp, &hops, parts, [&](int part, u64 w_lo, u64 w_hi) -> int {
+        CK(cudaEventRecord(evs[(size_t)part], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copy_stream, evs[(size_t)part], 0));
+        if (w_hi > w_lo) CK(cudaMemcpyAsync(dest + w_lo, ctx->scratch32.p + w_lo, sizeof(int32_t) * (w_hi - w_lo), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        return FORA_OK;
+    });
+    cudaError_t ce = cudaStreamSynchronize(ctx->copy_stream);
+    for (auto& e : evs) cudaEventDestroy(e);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(dest, ctx->scratch32.p, sizeof(int32_t) * total, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (ce != cudaSuccess) return ctx->fail(FORA_ECUDA, std::string("index copy: ") + cudaGetErrorString(ce));
+    ctx->bulk_walks = total;
+    ctx->bulk_hops = hops;
+    ctx->bulk_kernel_ms = ctx->walk_kernel_ms - ms0;
+    return FORA_OK;
+}
+// walks, hops and walk-kernel milliseconds (CUDA events on the work stream) of the last fora_index_build call: roofline accounting
+extern "C" int fora_index_build_stat(fora_ctx* ctx, uint64_t* walks, uint64_t* hops, double* kernel_ms) {
+    if (!ctx) return FORA_EINVAL;
+    if (walks) *walks = ctx->bulk_walks;
+    if (hops) *hops = ctx->bulk_hops;
+    if (kernel_ms) *kernel_ms = ctx->bulk_kernel_ms;
     return FORA_OK;
 }
 

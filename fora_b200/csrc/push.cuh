@@ -60,9 +60,10 @@ __host__ __device__ __forceinline__ u32 entry_deg24(u64 e) { return (u32)(e >> 3
 __host__ __device__ __forceinline__ int32_t entry_vertex(u64 e) { return (int32_t)(u32)e; }
 
 struct PushCtl {
-    u32 fcount[3][MAX_SLOTS]; // per-slot frontier sizes, rotated by level % 3
+    u32 fcount[3][MAX_SLOTS]; // per-slot frontier sizes: push_kernel rotates by level % 3; push2 / tail kernels index [buffer][slot]
     u32 levels_run;
     u32 pad[3];
+    u32 par[MAX_SLOTS];       // push2 / tail kernels: which buffer (front0 / front1) holds the slot's current frontier
 };
 
 struct PushArgs {

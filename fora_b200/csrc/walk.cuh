@@ -258,7 +258,12 @@ struct WalkArgs {
     int slot0;                        // first slot of this launch (blockIdx.y counts from it)
     u64 hot_elems;                    // HINT instantiation: neighbour slots from this position on are loaded with L2 evict_first
     int debug_no_red;                 // development ablation only (FORA_DEBUG_NO_RED): skip the ppr accumulation, results are WRONG
+    // OUT != 0 (bulk walks: index build, Monte-Carlo, BiPPR, test hook): where the destinations go instead of ppr
+    int32_t* out_dest;                // OUT_DEST: out_dest[global walk index] = destination (through new2old when set)
+    u64* out_counts;                  // OUT_COUNT: out_counts[destination] += 1 (internal ids)
+    const int32_t* __restrict__ new2old;
 };
+enum { OUT_PPR = 0, OUT_DEST = 1, OUT_COUNT = 2 };
 
 // The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
 // step first stops with probability alpha (skipped once when NO_ZERO_HOP), then moves to a uniform
@@ -276,7 +281,9 @@ struct WalkArgs {
 // own way -- fetch, next Philox block -- while its warp-mates were still stepping, and the warp never met again:
 // 13.7 of 32 lanes active per issued instruction, 89 G hops/s; converged: 18.9 lanes, 97 G hops/s.)
 // HINT: neighbour slots at positions >= hot_elems of the (hot-first) column array are loaded with L2 evict_first.
-template <typename OffT, bool NO_ZERO_HOP, bool HINT>
+// OUT selects what happens with a destination: OUT_PPR ppr[dest] += inc_v (the query path), OUT_DEST store it at the walk's global
+// index (index build, build.h:344-354; test hook), OUT_COUNT count it (montecarlo_query / bippr_query, query.h:25-31, 81-88).
+template <typename OffT, bool NO_ZERO_HOP, bool HINT, int OUT = OUT_PPR>
 __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<OffT> g) {
     // walk offsets of the sources touching the chunk, relative to the chunk start.  Entries 1.. lie in (0, chunk] and fit
     // 16 bits; entry 0 (<= 0, a source that started in an earlier chunk, possibly billions of walks ago) keeps 64 bits.
@@ -329,9 +336,18 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
         __syncthreads();
 
         int32_t cur = 0, start = 0;
-        u32 jlo = 0, jhi = 0, blk = 0;
+        u32 jlo = 0, jhi = 0, blk = 0, myx = 0;
         double inc = 0.0;
         bool have = false, first = false, more = true;
+        auto deliver = [&](int32_t dest, u32 x) { // one walk has ended at `dest`
+            if (OUT == OUT_PPR) {
+                if (!a.debug_no_red) atomicAdd(&ppr[dest], inc);
+            } else if (OUT == OUT_DEST) {
+                a.out_dest[w0 + x] = a.new2old ? a.new2old[dest] : dest;
+            } else {
+                atomicAdd(&a.out_counts[dest], 1ull);
+            }
+        };
         for (;;) {
             __syncwarp();
             while (!have && more) { // refill; a walk resolved without walking (index hit / dangling start) fetches again
@@ -343,7 +359,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
                 const u32 own = s_own[x];
                 const u64 j = own ? (u64)(x - (u32)s_rel[own]) : (u64)((long long)x - s_rel0);
                 const int32_t v = srcs[s_lo + own];
-                inc = incs[s_lo + own];
+                if (OUT == OUT_PPR) inc = incs[s_lo + own];
                 bool done = false;
                 int32_t dest = v;
                 if (a.with_idx) { // query.h:290-307: the first min(n_v, count) walks come from the index
@@ -357,9 +373,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
                 }
                 if (!done && (u32)(g.ptr[v + 1] - g.ptr[v]) == 0) done = true; // algo.h:127-129
                 if (done) {
-                    if (!a.debug_no_red) atomicAdd(&ppr[dest], inc);
+                    deliver(dest, x);
                 } else {
                     cur = start = v;
+                    myx = x;
                     jlo = (u32)j;
                     jhi = (u32)(j >> 32);
                     blk = 0;
@@ -376,7 +393,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
                     const u32 r_stop = half ? rnd.z : rnd.x;
                     const u32 r_pick = half ? rnd.w : rnd.y;
                     if (!first && r_stop < a.alpha_thr) { // algo.h:131-133
-                        if (!a.debug_no_red) atomicAdd(&ppr[cur], inc);
+                        deliver(cur, myx);
                         have = false;
                         break;
                     }
@@ -401,76 +418,6 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
         if (my_hops) atomicAdd(&a.hops[slot], my_hops);
         if (my_hits) atomicAdd(&a.idx_hits[slot], my_hits);
     }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Bulk walk destinations from explicit (start, count) segments: test hook (random_walk x count),
-// Monte-Carlo baseline (omega walks from s, query.h:25-31) and index build (build.h:344-354).
-// Walk `j` of a segment starting at global position `base` writes dest[base + j] and/or counts it.
-// ---------------------------------------------------------------------------------------------
-struct BulkArgs {
-    u32 alpha_thr, seed_lo, seed_hi;
-    u32 key_tag;                       // distinguishes index build / MC / test streams
-    const u64* __restrict__ seg_off;   // [nseg+1] exclusive prefix of counts, relative to v_begin's offset
-    int32_t v_begin;                   // segment i walks from vertex v_begin + i (or from `single` if >= 0)
-    int32_t single;
-    u64 nseg;
-    u64 total;
-    int32_t* __restrict__ dest;        // may be null
-    u64* __restrict__ counts;          // [n] destination histogram, may be null
-    u64* __restrict__ hops;            // [1]
-    const int32_t* __restrict__ old2new; // internal relabelling (null: identity): starts arrive / destinations leave in original ids
-    const int32_t* __restrict__ new2old;
-};
-
-template <typename OffT, bool NO_ZERO_HOP>
-__global__ void __launch_bounds__(WALK_THREADS) bulk_walk_kernel(BulkArgs a, CsrView<OffT> g) {
-    const u32 k0 = a.seed_lo ^ (a.key_tag * 0x9E3779B9u), k1 = a.seed_hi ^ 0x5bd1e995u;
-    u64 my_hops = 0;
-    for (u64 w = blockIdx.x * (u64)WALK_THREADS + threadIdx.x; w < a.total; w += (u64)gridDim.x * WALK_THREADS) {
-        int32_t start;
-        u64 j;
-        if (a.single >= 0) {
-            start = a.single;
-            j = w;
-        } else { // segment of w: last i with seg_off[i] <= w
-            u64 lo = 0, hi = a.nseg;
-            while (hi - lo > 1) {
-                const u64 mid = (lo + hi) >> 1;
-                if (a.seg_off[mid] <= w) lo = mid;
-                else hi = mid;
-            }
-            start = a.v_begin + (int32_t)lo;
-            j = w - a.seg_off[lo];
-        }
-        int32_t cur = a.old2new ? a.old2new[start] : start; // Philox stays keyed by the ORIGINAL start id
-        const int32_t home = cur;
-        OffT b = g.ptr[cur];
-        u32 d = (u32)(g.ptr[cur + 1] - b);
-        if (d != 0) {
-            bool first = NO_ZERO_HOP;
-            u32 blk = 0;
-            for (;;) {
-                const Philox4 rnd = philox4x32_10((u32)j, (u32)(j >> 32), blk++, (u32)start, k0, k1);
-                // two steps per Philox call
-                if (!first && rnd.x < a.alpha_thr) break;
-                first = false;
-                if (d) { cur = __ldg(&g.col[b + (OffT)__umulhi(rnd.y, d)]); ++my_hops; }
-                else cur = home;
-                b = g.ptr[cur];
-                d = (u32)(g.ptr[cur + 1] - b);
-                if (rnd.z < a.alpha_thr) break;
-                if (d) { cur = __ldg(&g.col[b + (OffT)__umulhi(rnd.w, d)]); ++my_hops; }
-                else cur = home;
-                b = g.ptr[cur];
-                d = (u32)(g.ptr[cur + 1] - b);
-            }
-        }
-        if (a.dest) a.dest[w] = a.new2old ? a.new2old[cur] : cur;
-        if (a.counts) atomicAdd(&a.counts[cur], 1ull); // histogram stays in internal ids
-    }
-    my_hops = warp_sum(my_hops);
-    if (lane_id() == 0 && my_hops) atomicAdd(a.hops, my_hops);
 }
 
 // ppr[v] = counts[v] * 1.0 / omega   (query.h:35-38)

@@ -157,6 +157,15 @@ int fora_compute_ppr(fora_ctx* ctx, const double* reserve, const double* residue
  * stats: host fora_query_stat[n_q] or NULL.  timing may be NULL. */
 int fora_query_batch(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, double* ppr,
                      fora_query_stat* stats, fora_batch_timing* timing);
+/* The same queries with a COMPACTED result: for query i the (node id, value) pairs of every entry >= threshold (unordered) at
+ * ids/values[offsets[i] .. offsets[i+1]).  The reference never ships the vector anywhere (query.h:1471-1476); FORA's guarantee
+ * covers pi >= delta = 1/n only (algo.h:455-463), so threshold = 1/n keeps everything the guarantee speaks about at a few per
+ * cent of the dense vector's bytes.  ids/values: host buffers of cap_total entries (pinned memory makes the copies overlap the
+ * next wave); offsets: host uint64[n_q+1].  FORA_ERANGE when a query yields more than cap_per_query entries or the batch more
+ * than cap_total. */
+int fora_query_batch_sparse(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, double threshold, uint64_t cap_per_query,
+                            uint64_t cap_total, int32_t* ids, double* values, uint64_t* offsets, fora_query_stat* stats,
+                            fora_batch_timing* timing);
 /* Same work with inputs/outputs resident in HBM: sources device int32[n_q]; the PPR vectors stay
  * on the device (last `slots` queries readable through fora_device_ppr). */
 int fora_query_batch_device(fora_ctx* ctx, int algo, const int32_t* d_sources, int32_t n_q,
@@ -198,6 +207,9 @@ int fora_index_info(fora_ctx* ctx, uint64_t* offsets, uint64_t* counts, uint64_t
  * [offsets[v_begin], offsets[v_end]) (host int32).  Sharding by source range = multi-GPU build. */
 int fora_index_build(fora_ctx* ctx, const uint64_t* offsets, const uint64_t* counts, int32_t v_begin, int32_t v_end,
                      int32_t* dest);
+/* walks, neighbour hops and walk-kernel milliseconds (CUDA events) of the last fora_index_build call on this ctx (the reference
+ * prints only wall-clock build time, build.h:360-363; these feed the roofline line of the index build) */
+int fora_index_build_stat(fora_ctx* ctx, uint64_t* walks, uint64_t* hops, double* kernel_ms);
 int fora_index_upload(fora_ctx* ctx, const uint64_t* offsets, const uint64_t* counts, const int32_t* dest, uint64_t len);
 
 /* ------------------------------------------------------------------------------------------

@@ -39,8 +39,8 @@ for slots in slot_list:
             lv = sum(s["push_levels"] for s in stats) / nq
             hops = sum(s["walk_hops"] for s in stats) / nq
             print("slots %2d balanced %d: %6.1f q/s | push kernel %.3f ms/q (%.1f G edges/s, %.1fM edges, %.0f levels) push phase %.3f | walk kernel %.3f ms/q (%.1f G hops/s)" % (
-                slots, bal, nq / (tm["total_ms"] * 1e-3), tm["push_kernel_ms"] / nq, ed / tm["push_kernel_ms"] * nq / 1e6 / nq, ed / 1e6, lv,
-                tm["push_ms"] / nq, tm["walk_kernel_ms"] / nq, hops / tm["walk_kernel_ms"] * nq / 1e6 / nq), flush=True)
+                slots, bal, nq / (tm["total_ms"] * 1e-3), tm["push_kernel_ms"] / nq, ed / (tm["push_kernel_ms"] / nq) / 1e6, ed / 1e6, lv,
+                tm["push_ms"] / nq, tm["walk_kernel_ms"] / nq, hops / (tm["walk_kernel_ms"] / nq) / 1e6), flush=True)
         if TRACE and slots <= 4:
             E.query_batch("fora", queries[:slots], want_ppr=False)  # non-balanced: one launch holds every level
             out = np.zeros(4 * 4096, np.uint64)
