@@ -44,6 +44,14 @@ class QueryStat(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
+class SplitTiming(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("push_ms", C.c_float), ("bcast_ms", C.c_float), ("walk_ms", C.c_float), ("reduce_ms", C.c_float),
+                ("n_gpus", C.c_uint32), ("bcast_bytes", C.c_uint64), ("reduce_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {f: getattr(self, f) for f, _ in self._fields_}
+
+
 class BatchTiming(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("push_ms", C.c_float), ("walk_ms", C.c_float), ("plan_ms", C.c_float),
                 ("topk_ms", C.c_float), ("copy_ms", C.c_float), ("kernel_launches", C.c_uint64),
@@ -134,6 +142,14 @@ def lib():
     L.fora_index_upload.argtypes = [vp, c_up, c_up, c_ip, C.c_uint64]
     L.fora_index_build_stat.argtypes = [vp, c_up, c_up, c_dp]
     L.fora_power_iteration.argtypes = [vp, C.c_int32, C.c_int, c_dp]
+    L.fora_group_create.argtypes = [C.c_int, c_ip, C.c_uint64, C.POINTER(vp)]
+    L.fora_group_destroy.argtypes = [vp]
+    L.fora_group_size.argtypes = [vp]
+    L.fora_group_ctx.restype = vp
+    L.fora_group_ctx.argtypes = [vp, C.c_int]
+    L.fora_group_last_error.restype = C.c_char_p
+    L.fora_group_last_error.argtypes = [vp]
+    L.fora_group_query_split.argtypes = [vp, C.c_int32, C.c_uint32, c_dp, C.POINTER(QueryStat), C.POINTER(SplitTiming)]
     _lib = L
     return L
 
@@ -414,3 +430,54 @@ class Engine:
         ppr = np.empty(self.n)
         self._ck(self.L.fora_power_iteration(self.h, source, iters, _p(ppr, c_dp)))
         return ppr
+
+
+class Group:
+    """Several GPUs of one box answering ONE whole-graph query together (fora_group_*, include/fora_b200.h): the library itself
+    issues the NCCL broadcast of the compacted push state and the all-reduce of the dense vectors."""
+
+    def __init__(self, n_gpus, seed=1, devices=None):
+        self.L = lib()
+        self.h = C.c_void_p()
+        dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
+        rc = self.L.fora_group_create(n_gpus, _p(dev, c_ip), seed, C.byref(self.h))
+        if rc:
+            raise ForaError("fora_group_create failed: %s" % self.L.fora_group_last_error(None).decode())
+        self.engines = []
+        for i in range(n_gpus):  # views of the group's contexts (owned by the group)
+            E = Engine.__new__(Engine)
+            E.L, E.h, E.n, E.m_decl, E.params = self.L, C.c_void_p(self.L.fora_group_ctx(self.h, i)), 0, 0, Params()
+            E.close = lambda: None
+            self.engines.append(E)
+
+    def upload_graph(self, n, m_decl, out_ptr, out_col):
+        for E in self.engines:
+            E.upload_graph(n, m_decl, out_ptr, out_col)
+
+    def configure(self, *a, **kw):
+        r = None
+        for E in self.engines:
+            r = E.configure(*a, **kw)
+        return r
+
+    def query_split(self, source, query_id=0, want_ppr=True):
+        n = self.engines[0].n
+        ppr = np.empty(n) if want_ppr else None
+        st, tm = QueryStat(), SplitTiming()
+        rc = self.L.fora_group_query_split(self.h, int(source), int(query_id), _p(ppr, c_dp), C.byref(st), C.byref(tm))
+        if rc:
+            raise ForaError("rc=%d: %s" % (rc, self.L.fora_group_last_error(self.h).decode()))
+        return ppr, st.as_dict(), tm.as_dict()
+
+    def close(self):
+        if getattr(self, "h", None):
+            for E in self.engines:
+                E.h = None
+            self.L.fora_group_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -129,6 +129,8 @@ struct fora_ctx {
     DevBuf<double> ppr;      // top-k rounds: ppr is rebuilt from reserve every round (query.h:533)
     DevBuf<double> ub, lb;   // non --opt top-k: per-node upper / lower PPR bounds (algo.h:48-49)
     DevBuf<unsigned char> in_topk;
+    DevBuf<int32_t> stop_slots;
+    DevBuf<double> stop_lowk;
     DevBuf<u32> flags;
     // batched select (topk.cuh): per-vector state, candidate lists, output lists
     DevBuf<SelSlot> sel_st;
@@ -156,11 +158,15 @@ struct fora_ctx {
     int push_grid = 0;
     // second-generation push (push2.cuh): sub-waves of push_sub slots, tails per slot
     int push_v = 1, push_sub = 2, push2_grid = 0, push_prefetch = 1;
+    u32 push_hot = 0;          // vertices per slot whose residue atomics carry evict_last (0: all of them)
+    u32 push_cold_policy = 0;
+    size_t persist_now = (size_t)-1, persist_walk = 0; // current persisting carve-out / the one the walk phase wants
     int push_win = 1;          // pin the sub-wave's residue vectors with an access-policy window (persisting L2 lines)
     int push_win_reset = 0;    // cudaCtxResetPersistingL2Cache after the push phase
     size_t push_carve = 0;     // persisting carve-out while push2 runs
     u32 tail_nf = 1024, tail_e = 8192;
     DevBuf<u32> hubbuf;
+    DevBuf<u64> front_begs;
     // bulk walks (index build / Monte-Carlo / BiPPR) through the chunked walk kernel
     DevBuf<u32> bulk_chunk_first;
     DevBuf<unsigned char> bulk_meta;
@@ -208,6 +214,7 @@ struct fora_ctx {
     } while (0)
 
 static int relabel_graph(fora_ctx* ctx);
+static int set_persist_limit(fora_ctx* ctx, size_t bytes);
 static int pack_columns(fora_ctx* ctx);
 static int permute_csr(fora_ctx* ctx, int32_t n, int64_t ne, const int32_t* src_of, const int32_t* map, const int64_t* in_ptr,
                        const int32_t* in_col, int64_t** out_ptr, int32_t** out_col);
@@ -291,9 +298,9 @@ extern "C" void fora_ctx_destroy(fora_ctx* ctx) {
     ctx->log_v.release(); ctx->log_r.release(); ctx->log_cur.release();
     ctx->sp_ids.release(); ctx->sp_vals.release(); ctx->sp_cnt.release();
     for (auto& e : ctx->ev_sp) if (e) cudaEventDestroy(e);
-    ctx->hubbuf.release(); ctx->bulk_chunk_first.release(); ctx->bulk_meta.release(); ctx->bulk_small.release(); ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
+    ctx->hubbuf.release(); ctx->front_begs.release(); ctx->bulk_chunk_first.release(); ctx->bulk_meta.release(); ctx->bulk_small.release(); ctx->inc.release(); ctx->eoff.release(); ctx->block_sum.release(); ctx->trace.release(); ctx->ctl.release(); ctx->meta.release();
     ctx->part_sum.release(); ctx->part_nnz.release(); ctx->blk_src.release(); ctx->blk_walk.release();
-    ctx->ppr.release(); ctx->ub.release(); ctx->lb.release(); ctx->in_topk.release(); ctx->flags.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
+    ctx->ppr.release(); ctx->ub.release(); ctx->lb.release(); ctx->in_topk.release(); ctx->stop_slots.release(); ctx->stop_lowk.release(); ctx->flags.release(); ctx->stage.release(); ctx->idx_used.release(); ctx->srcs.release(); ctx->woff.release(); ctx->incs.release(); ctx->chunk_first.release();
     ctx->idx_off.release(); ctx->idx_cnt.release(); ctx->idx_dest.release();
     ctx->sel_st.release(); ctx->sel_res.release(); ctx->sel_slots.release(); ctx->sel_ci.release(); ctx->sel_on.release(); ctx->sel_ck.release(); ctx->sel_ov.release();
     ctx->counts.release(); ctx->bwd_res.release(); ctx->bwd_rv.release(); ctx->bwd_lists.release(); ctx->scratch64.release(); ctx->scratch32.release(); ctx->scratchd.release();
@@ -832,9 +839,14 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
                 // columns / frontier / log traffic of a level (~2x the vectors' size) evicts them (L2 hit rate 45 %, r2b ncu)
                 ctx->push_carve = getenv("FORA_PUSH_CARVE_MB") ? (size_t)atol(getenv("FORA_PUSH_CARVE_MB")) << 20 : ctx->l2_persist_max;
                 ctx->push_carve = std::min(ctx->push_carve, ctx->l2_persist_max);
-                limit = std::max(limit, ctx->push_carve);
             }
-            if (ctx->l2_persist_max) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, limit);
+            ctx->persist_walk = limit;
+            ctx->push_hot = getenv("FORA_PUSH_HOT") ? (u32)atol(getenv("FORA_PUSH_HOT")) : 0u;
+            ctx->push_cold_policy = getenv("FORA_PUSH_COLD") ? (u32)atoi(getenv("FORA_PUSH_COLD")) : 0u;
+            if (ctx->push_hot && !fits && !ctx->push_carve) ctx->push_carve = ctx->l2_persist_max;
+            if (fits) { ctx->push_carve = 0; limit = ctx->l2_persist_max; ctx->persist_walk = limit; }
+            int lrc = set_persist_limit(ctx, ctx->persist_walk);
+            if (lrc) return lrc;
         }
         CK(ctx->front0.ensure(fcap));
         CK(ctx->front1.ensure(fcap));
@@ -882,6 +894,7 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         ctx->push_prefetch = getenv("FORA_PUSH_PREFETCH") ? atoi(getenv("FORA_PUSH_PREFETCH")) : 1;
         ctx->tail_nf = std::min<u32>(TAIL_NF_CAP, getenv("FORA_TAIL_NF") ? (u32)atoi(getenv("FORA_TAIL_NF")) : 1024u);
         ctx->tail_e = getenv("FORA_TAIL_E") ? (u32)atoi(getenv("FORA_TAIL_E")) : 8192u;
+        CK(ctx->front_begs.ensure(n * (size_t)std::min(S, P2_MAX_SUB))); // a sub-wave's frontier at most
         CK(ctx->hubbuf.ensure(2 * P2_HUB_CAP + 2));
         CK(cudaMemsetAsync(ctx->hubbuf.p, 0, sizeof(u32) * (2 * P2_HUB_CAP + 2), ctx->stream));
         int per_sm2 = 0;
@@ -906,6 +919,16 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
     return FORA_OK;
 }
 
+// The persisting carve-out is a device-wide limit: the push phase wants it large (hot residue prefixes / a sub-wave's vectors),
+// the walk phase small (row offsets only -- what is set aside is lost to the walks' normal traffic).  Switched per phase.
+static int set_persist_limit(fora_ctx* ctx, size_t bytes) {
+    if (!ctx->l2_persist_max || !ctx->l2_policy) return FORA_OK;
+    bytes = std::min(bytes, ctx->l2_persist_max);
+    if (bytes == ctx->persist_now) return FORA_OK;
+    CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, bytes));
+    ctx->persist_now = bytes;
+    return FORA_OK;
+}
 // Pin [arena+off, +bytes) in L2 for the kernels launched next on the work stream (bytes == 0 clears).
 static int set_l2_window(fora_ctx* ctx, size_t off, size_t bytes, size_t carve = 0) {
     if (!ctx->l2_policy || bytes == 0) return FORA_OK;
@@ -1010,6 +1033,8 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     a.log_cur = ctx->log_cur.p;
     a.colx = ctx->g.deg_shift ? ctx->g.out_colx : nullptr;
     a.deg_shift = ctx->g.deg_shift;
+    a.hot_limit = ctx->push_hot;
+    a.cold_policy = ctx->push_cold_policy;
     return a;
 }
 
@@ -1032,6 +1057,7 @@ static int launch_push(fora_ctx* ctx, bool defer_log = false) {
     ctx->level_base += (1u << 20);
     int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
     if (wrc) return wrc;
+    if (ctx->push_carve && (wrc = set_persist_limit(ctx, ctx->push_carve))) return wrc;
     kev_begin(ctx, 0);
     if (ctx->g.off32) {
         CsrView<u32> v{ctx->hot_ptr32, ctx->g.out_col};
@@ -1057,6 +1083,7 @@ static int launch_push2(fora_ctx* ctx, bool defer_log) {
     a.tail_nf = ctx->tail_nf;
     a.tail_e = ctx->tail_e;
     a.rv = ctx->inc.p;
+    a.begs = ctx->front_begs.p;
     a.hub = ctx->hubbuf.p;
     a.hub_cnt = ctx->hubbuf.p + 2 * P2_HUB_CAP;
     a.force = m->force;
@@ -1066,6 +1093,7 @@ static int launch_push2(fora_ctx* ctx, bool defer_log) {
     const int S = ctx->slots, K = ctx->push_sub;
     int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
     if (wrc) return wrc;
+    if (ctx->push_carve && (wrc = set_persist_limit(ctx, ctx->push_carve))) return wrc;
     auto tail = [&]() -> int {
         a.slot0 = 0;
         a.k = S;
@@ -1098,7 +1126,7 @@ static int launch_push2(fora_ctx* ctx, bool defer_log) {
             if (!need) continue;
             a.slot0 = s0;
             a.k = k;
-            if (ctx->push_carve) { // this sub-wave's residue vectors become the persisting part of the L2
+            if (ctx->push_carve && ctx->push_win && ctx->push_v == 2) { // this sub-wave's residue vectors become the persisting part of the L2
                 int w2 = set_l2_window(ctx, (size_t)((unsigned char*)(ctx->residue.p + (size_t)s0 * ctx->g.n) - ctx->arena.p), sizeof(double) * (size_t)k * ctx->g.n, ctx->push_carve);
                 if (w2) return w2;
             }
@@ -1289,6 +1317,10 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.hot_elems = (u64)((getenv("FORA_WALK_HOT_MB") ? atof(getenv("FORA_WALK_HOT_MB")) : 32.0) * 262144.0);
     wa.debug_no_red = getenv("FORA_DEBUG_NO_RED") ? atoi(getenv("FORA_DEBUG_NO_RED")) : 0;
     const int wgx = ctx->num_sms * (getenv("FORA_WALK_GRID") ? atoi(getenv("FORA_WALK_GRID")) : 16);
+    {
+        int lrc = set_persist_limit(ctx, ctx->persist_walk);
+        if (lrc) return lrc;
+    }
     if (ppr == ctx->reserve.p) {
         int wrc = set_l2_window(ctx, ctx->win_walk_off, ctx->win_walk_bytes);
         if (wrc) return wrc;
@@ -2067,8 +2099,8 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
             CK(ctx->ppr.ensure(nn * S));
             CK(ctx->ub.ensure(nn * S));
             CK(ctx->lb.ensure(nn * S));
-            CK(ctx->in_topk.ensure(nn));
-            CK(ctx->flags.ensure(4));
+            CK(ctx->in_topk.ensure(nn * S)); // one byte map per slot: the bound tests of a round run for all slots at once
+            CK(ctx->flags.ensure(2 * MAX_SLOTS));
             const bool use_idx = keep.with_idx && ctx->has_index;
             if (use_idx) {
                 CK(ctx->idx_used.ensure(nn * S));
@@ -2084,7 +2116,7 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
             fill_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->ub.p, nn * cnt, 1.0); // upper_bounds.reset_one_values(), query.h:940
             CKL();
             CK(cudaMemsetAsync(ctx->lb.p, 0, sizeof(double) * nn * cnt, ctx->stream));          // lower_bounds.reset_zero_values()
-            CK(cudaMemsetAsync(ctx->in_topk.p, 0, nn, ctx->stream));
+            CK(cudaMemsetAsync(ctx->in_topk.p, 0, nn * cnt, ctx->stream));
             CK(cudaMemcpyAsync(ctx->ppr.p, ctx->reserve.p, sizeof(double) * nn * cnt, cudaMemcpyDeviceToDevice, ctx->stream));
             const double pfail = 1.0 / n / n / log((double)n);                               // query.h:915
             const double threshold = (1.0 - 0.77) / pow(500, 0.77) / pow((double)n, 1 - 0.77); // query.h:913, ppr_decay_alpha = 0.77
@@ -2116,14 +2148,22 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
                 for (int s = 0; s < cnt; ++s) {
                     if (done[s]) continue;
                     tot_walks[s] += h->nwalk[s]; tot_hits[s] += h->idx_hits[s]; tot_hops[s] += h->hops[s];
-                    const double rsum_s = h->rsum[s];
-                    const double real_rw = (double)h->nwalk[s];
-                    if (delta < threshold && real_rw > 0 && rsum_s > 0) { // set_ppr_bounds, query.h:745-746
-                        ppr_bounds_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, rsum_s, pfail, real_rw, ctx->ppr.p + nn * s, ctx->reserve.p + nn * s,
-                                                                                   ctx->ub.p + nn * s, ctx->lb.p + nn * s);
-                        CKL();
-                    }
                     act.push_back(s);
+                }
+                // set_ppr_bounds of every active slot in one launch (query.h:745-746; the per-slot scalars are read on the device)
+                CK(ctx->sel_slots.ensure(MAX_SLOTS));
+                CK(ctx->stop_slots.ensure(MAX_SLOTS));
+                CK(ctx->stop_lowk.ensure(MAX_SLOTS));
+                CK(ctx->flags.ensure(2 * MAX_SLOTS));
+                if (!act.empty()) {
+                    int32_t ids[MAX_SLOTS];
+                    for (size_t j = 0; j < act.size(); ++j) ids[j] = act[j];
+                    CK(cudaMemcpyAsync(ctx->stop_slots.p, ids, sizeof(int32_t) * act.size(), cudaMemcpyHostToDevice, ctx->stream));
+                    CK(cudaStreamSynchronize(ctx->stream)); // ids lives on this stack frame
+                    const int gx = std::max(1, std::min(ctx->num_sms * 8 / (int)act.size() + 1, (n + 255) / 256));
+                    ppr_bounds_kernel<<<dim3(gx, (unsigned)act.size()), 256, 0, ctx->stream>>>(n, nn, ctx->stop_slots.p, ctx->meta.p->rsum, ctx->meta.p->nwalk, pfail, delta, threshold,
+                                                                                            ctx->ppr.p, ctx->reserve.p, ctx->ub.p, ctx->lb.p);
+                    CKL();
                 }
                 // if_stop(), algo.h:1096-1166: k-th estimate of every active slot in one batched select ...
                 std::vector<SelResult> sres(MAX_SLOTS);
@@ -2133,25 +2173,31 @@ extern "C" int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, 
                     if (sel_kth(sres[j]) >= 2.0 * delta) stop[act[j]] = 1;
                     else if (!(delta >= threshold)) need_lb.push_back(act[j]);
                 }
-                // ... then the k largest lower bounds of the slots that are still open
+                // ... then the k largest lower bounds of the slots that are still open, and the bound tests of all of them in three launches
                 if ((rc = select_batch(ctx, ctx->lb.p, nn, need_lb.data(), (int)need_lb.size(), k, false, sres.data()))) return restore(rc);
-                for (size_t j = 0; j < need_lb.size(); ++j) {
-                    const int s = need_lb[j];
-                    const int32_t* d_nodes = ctx->sel_on.p + (size_t)ctx->sel_p2 * j;
-                    const u32 got = sres[j].out_count;
-                    const double low_k = sel_kth(sres[j]);
-                    // fewer than k positive lower bounds: some top-k node has lower bound 0 => ratio test fails (algo.h:1129-1134)
-                    if (got == k && low_k > delta) {
-                        CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(u32) * 4, ctx->stream));
-                        stop_mark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->ub.p + nn * s, ctx->lb.p + nn * s, keep.epsilon, ctx->in_topk.p, ctx->flags.p);
-                        stop_tail_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(n, ctx->ppr.p + nn * s, ctx->ub.p + nn * s, ctx->lb.p + nn * s, ctx->in_topk.p, low_k,
-                                                                                  keep.epsilon, ctx->flags.p);
-                        stop_unmark_kernel<<<4, 256, 0, ctx->stream>>>(d_nodes, k, ctx->in_topk.p);
+                {
+                    // only slots with k positive lower bounds above delta can pass (fewer: some top-k node has lower bound 0, algo.h:1129-1134)
+                    std::vector<int> test_j;
+                    for (size_t j = 0; j < need_lb.size(); ++j)
+                        if (sres[j].out_count == k && sel_kth(sres[j]) > delta) test_j.push_back((int)j);
+                    if (!test_j.empty()) {
+                        // the select left vector j's nodes at sel_on + j*sel_p2; the stop kernels index lists by position in need_lb
+                        int32_t ids[MAX_SLOTS];
+                        double lowk[MAX_SLOTS];
+                        for (size_t j = 0; j < need_lb.size(); ++j) { ids[j] = need_lb[j]; lowk[j] = sel_kth(sres[j]); }
+                        CK(cudaMemcpyAsync(ctx->stop_slots.p, ids, sizeof(int32_t) * need_lb.size(), cudaMemcpyHostToDevice, ctx->stream));
+                        CK(cudaMemcpyAsync(ctx->stop_lowk.p, lowk, sizeof(double) * need_lb.size(), cudaMemcpyHostToDevice, ctx->stream));
+                        CK(cudaMemsetAsync(ctx->flags.p, 0, sizeof(u32) * 2 * MAX_SLOTS, ctx->stream));
+                        const unsigned nj = (unsigned)need_lb.size();
+                        const int gx = std::max(1, std::min(ctx->num_sms * 8 / (int)nj + 1, (n + 255) / 256));
+                        stop_mark_kernel<<<dim3(4, nj), 256, 0, ctx->stream>>>(ctx->sel_on.p, ctx->sel_p2, k, ctx->stop_slots.p, nn, ctx->ub.p, ctx->lb.p, keep.epsilon, ctx->in_topk.p, ctx->flags.p);
+                        stop_tail_kernel<<<dim3(gx, nj), 256, 0, ctx->stream>>>(n, ctx->stop_slots.p, nn, ctx->ppr.p, ctx->ub.p, ctx->lb.p, ctx->in_topk.p, ctx->stop_lowk.p, keep.epsilon, ctx->flags.p);
+                        stop_unmark_kernel<<<dim3(4, nj), 256, 0, ctx->stream>>>(ctx->sel_on.p, ctx->sel_p2, k, ctx->stop_slots.p, nn, ctx->in_topk.p);
                         ctx->launches += 3;
-                        u32 hf[2];
-                        CK(cudaMemcpyAsync(hf, ctx->flags.p, sizeof(u32) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+                        u32 hf[2 * MAX_SLOTS];
+                        CK(cudaMemcpyAsync(hf, ctx->flags.p, sizeof(u32) * 2 * nj, cudaMemcpyDeviceToHost, ctx->stream));
                         CK(cudaStreamSynchronize(ctx->stream));
-                        stop[s] = !hf[0] && !hf[1];
+                        for (int j : test_j) stop[need_lb[(size_t)j]] = !hf[2 * j] && !hf[2 * j + 1];
                     }
                 }
                 for (int s : act)
@@ -2480,3 +2526,8 @@ extern "C" int fora_debug_push_trace(fora_ctx* ctx, uint64_t* out, int cap_level
     cudaMemcpy(out, ctx->trace.p, sizeof(u64) * 4 * lv, cudaMemcpyDeviceToHost);
     return lv;
 }
+
+// =============================================================================================
+// several GPUs on one query (NCCL)
+// =============================================================================================
+#include "group.cuh"

@@ -42,8 +42,10 @@ constexpr int P2_WQ = 256;             // per-warp queue of crossing vertices
 #define CFG_P2_HUB_DEG 256
 #endif
 constexpr u32 P2_HUB_DEG = CFG_P2_HUB_DEG; // out-degree from which a frontier vertex is cut across the whole grid (a warp walks <= 2 steps per entry)
-constexpr u32 P2_HUB_CAP = 4096;       // hub entries per level (a full list leaves the rest to the per-warp path: slow, correct)
-constexpr u32 P2_HUB_SM = 1024;        // hub entries staged in shared memory at a time (one per thread)
+constexpr u32 P2_HUB_CAP = 1024;       // hub entries per level = what one CTA stages in shared memory, one per thread (a full list leaves
+                                       // the rest to the per-warp path: slow, correct)
+constexpr u32 P2_HUB_SM = P2_HUB_CAP;
+constexpr u32 P2_CYC = 4;              // phase B hands 32-entry groups to the CTAs block-cyclically, P2_CYC consecutive groups at a time
 constexpr int P2_MAX_SUB = 8;          // slots per sub-wave handled by one push2 launch
 constexpr int TAIL_THREADS = 1024;
 constexpr u32 TAIL_NF_CAP = 2048;      // frontier entries a tail CTA keeps in shared memory
@@ -53,6 +55,7 @@ struct Push2Args {
     int32_t slot0, k;      // this launch handles slots [slot0, slot0 + k)
     u32 tail_nf, tail_e;   // a level with <= tail_nf entries and <= tail_e edges belongs to the tail kernel
     double* rv;            // per frontier entry (global index within the launch): residue pushed; < 0: listed as a hub
+    void* begs;            // OffT per frontier entry: start of the vertex's adjacency list (loaded in phase A, off phase B's critical path)
     u32* hub;              // [2 * P2_HUB_CAP] frontier indices of hub entries, by level parity
     u32* hub_cnt;          // [2]
     u32* force;            // [MAX_SLOTS] set by the tail kernel when it refused a level for its edge count
@@ -127,6 +130,7 @@ __device__ __forceinline__ void p2_scatter(const Push2Args& a, const CsrView<Off
     const PushArgs& p = a.p;
     const int lane = lane_id();
     u64* myq = sm.wqueue[w];
+    const u64 pol_cold = p.cold_policy ? pol_stream : l2_policy_evict_normal();
     const u32* off = WIDE ? sm.hb_off : sm.w_off[w];
     const u32* beg32 = WIDE ? sm.hb_beg32 : sm.w_beg32[w];
     const u32* beghi = WIDE ? sm.hb_beghi : sm.w_beghi[w];
@@ -185,7 +189,7 @@ __device__ __forceinline__ void p2_scatter(const Push2Args& a, const CsrView<Off
             du[k] = 0;
             if (ok[k]) {
                 double* rp = &p.residue[(size_t)(a.slot0 + rs[k]) * p.n + u[k]];
-                old[k] = p.l2_hints ? atomic_add_f64_hint(rp, inc[k], pol_keep) : atomicAdd(rp, inc[k]);
+                old[k] = p.l2_hints ? atomic_add_f64_hint(rp, inc[k], (p.hot_limit && (u32)u[k] >= p.hot_limit) ? pol_cold : pol_keep) : atomicAdd(rp, inc[k]);
                 if (dcode[k] != dmax) du[k] = (int32_t)dcode[k];
                 else du[k] = p.l2_hints ? ld_s32_hint(&p.deg[u[k]], pol_keep) : __ldg(&p.deg[u[k]]);
             }
@@ -337,6 +341,7 @@ __global__ void __launch_bounds__(P2_THREADS, 1) push2_kernel(Push2Args a, CsrVi
                     const size_t gi = (size_t)as * p.n + v;
                     p.reserve[gi] = __ldcg(&p.reserve[gi]) + r[q] * p.alpha;
                 }
+                __stcs(&((OffT*)a.begs)[idx[q]], d ? g.ptr[v] : (OffT)0);
                 double out = r[q];
                 if (d >= P2_HUB_DEG) {
                     const u32 pos = atomicAdd(&a.hub_cnt[hp], 1u);
@@ -385,64 +390,24 @@ __global__ void __launch_bounds__(P2_THREADS, 1) push2_kernel(Push2Args a, CsrVi
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             p.trace[4 * level + 3] = t;
         }
-        // ---- phase B: warps take 32-entry groups of the CTA's chunk and scatter their edges
-        for (;;) {
-            u32 gi = 0;
-            if (lane == 0) gi = atomicAdd(&sm.next_group, 1u);
-            gi = __shfl_sync(FULL, gi, 0);
-            const u32 i0 = lo_i + gi * WARP;
-            if (i0 >= hi_i) break;
-            const u32 i = i0 + lane;
-            const bool valid = i < hi_i;
-            u32 cnt = 0;
-            int rsl = 0;
-            double inc = 0.0;
-            OffT beg = 0;
-            bool dang = false;
-            if (valid) {
-                rsl = p2_slot_of(sm, k, i);
-                const u64 e = __ldcg(p2_front(p, a.slot0 + rsl, sm.par[rsl]) + (i - sm.fbase[rsl]));
-                const double r = __ldcg(&a.rv[i]);
-                const int32_t v = entry_vertex(e);
-                u32 d = entry_deg24(e);
-                if (d == DEG_SAT) d = (u32)__ldg(&p.deg[v]);
-                if (r > 0.0) { // r < 0: listed as a hub, handled by the whole grid below
-                    dang = d == 0;
-                    if (!dang) beg = g.ptr[v];
-                    inc = dang ? r * (1.0 - p.alpha) : ((1.0 - p.alpha) * r) / (double)d;
-                    cnt = dang ? 1u : d;
-                }
-            }
-            const u32 incl = warp_incl_scan(cnt);
-            const u32 T = __shfl_sync(FULL, incl, 31);
-            sm.w_off[w][lane] = incl - cnt;
-            if (lane == 31) sm.w_off[w][32] = incl;
-            sm.w_beg32[w][lane] = (u32)(u64)beg;
-            sm.w_beghi[w][lane] = (u32)((u64)beg >> 32);
-            sm.w_inc[w][lane] = inc;
-            sm.w_slot[w][lane] = dang ? ~rsl : rsl;
-            __syncwarp();
-            if (T) p2_scatter<OffT, false>(a, g, sm, ctl, w, 0u, T, wq, wq_slot, pol_keep, pol_stream);
-            __syncwarp();
-        }
-        // hubs: the listed entries are staged CTA-wide (one per thread), their edges form one line, every CTA takes one slice
-        // of it and its warps the 32*P2_UB-edge steps of that slice -- one dependent load chain per level, not one per hub
+        // ---- phase B.  Hubs first: the listed entries are staged CTA-wide (one per thread), their edges form one line and every
+        // CTA takes one slice of its 32*P2_UB-edge steps.  The steps and the CTA's 32-entry groups (handed out block-cyclically:
+        // the degree mix of neighbouring frontier entries is correlated) then form ONE work list that the warps drain on their
+        // own -- no CTA barrier below this point, a warp prefetches the entries of its next group while it scatters the current one.
         const u32 nh = min(*((volatile u32*)&a.hub_cnt[hp]), P2_HUB_CAP);
-        for (u32 h0 = 0; h0 < nh; h0 += P2_HUB_SM) {
-            const u32 nb = min(P2_HUB_SM, nh - h0);
-            __syncthreads(); // the previous batch has been consumed
+        u32 hub_steps = 0, hub_s0 = 0, EH = 0;
+        if (nh) {
             u32 d = 0;
-            if (threadIdx.x < nb) {
-                const u32 i = __ldcg(&a.hub[hp * P2_HUB_CAP + h0 + threadIdx.x]);
+            if (threadIdx.x < nh) {
+                const u32 i = __ldcg(&a.hub[hp * P2_HUB_CAP + threadIdx.x]);
                 const int rsl = p2_slot_of(sm, k, i);
                 const u64 e = __ldcg(p2_front(p, a.slot0 + rsl, sm.par[rsl]) + (i - sm.fbase[rsl]));
                 const double r = -__ldcg(&a.rv[i]);
-                const int32_t v = entry_vertex(e);
+                const u64 beg = (u64)__ldcg(&((const OffT*)a.begs)[i]);
                 d = entry_deg24(e);
-                if (d == DEG_SAT) d = (u32)__ldg(&p.deg[v]);
-                const OffT beg = g.ptr[v];
-                sm.hb_beg32[threadIdx.x] = (u32)(u64)beg;
-                sm.hb_beghi[threadIdx.x] = (u32)((u64)beg >> 32);
+                if (d == DEG_SAT) d = (u32)__ldg(&p.deg[entry_vertex(e)]);
+                sm.hb_beg32[threadIdx.x] = (u32)beg;
+                sm.hb_beghi[threadIdx.x] = (u32)(beg >> 32);
                 sm.hb_inc[threadIdx.x] = ((1.0 - p.alpha) * r) / (double)d;
                 sm.hb_slot[threadIdx.x] = rsl;
             }
@@ -452,19 +417,92 @@ __global__ void __launch_bounds__(P2_THREADS, 1) push2_kernel(Push2Args a, CsrVi
             const u32 wt = sm.hb_wtot[lane];
             const u32 wti = warp_incl_scan(wt);
             const u32 before = __shfl_sync(FULL, wti, w > 0 ? w - 1 : 0);
-            const u32 EH = __shfl_sync(FULL, wti, 31);
+            EH = __shfl_sync(FULL, wti, 31);
             sm.hb_off[threadIdx.x] = (w > 0 ? before : 0u) + incl - d;
             if (threadIdx.x == P2_THREADS - 1) sm.hb_off[P2_HUB_SM] = EH;
             __syncthreads();
-            const u32 step = WARP * P2_UB;
-            const u32 nsteps = (EH + step - 1) / step;
-            const u32 s_lo = (u32)(((u64)nsteps * c) / G), s_hi = (u32)(((u64)nsteps * (c + 1)) / G);
-            for (u32 st = s_lo + (u32)w; st < s_hi; st += P2_WARPS)
-                p2_scatter<OffT, true>(a, g, sm, ctl, w, st * step, min(EH, (st + 1) * step), wq, wq_slot, pol_keep, pol_stream, nb);
+            const u32 nsteps = (EH + WARP * P2_UB - 1) / (WARP * P2_UB);
+            hub_s0 = (u32)(((u64)nsteps * c) / G);
+            hub_steps = (u32)(((u64)nsteps * (c + 1)) / G) - hub_s0;
+        }
+        // this CTA's groups: global group j = ((i / P2_CYC) * G + c) * P2_CYC + i % P2_CYC for local index i
+        const u32 NG = (nf + WARP - 1) / WARP;
+        const u32 nblk = (NG + P2_CYC - 1) / P2_CYC;                      // blocks of P2_CYC groups
+        const u32 myblk = nblk > c ? (nblk - c + G - 1) / G : 0u;          // blocks c, c + G, ...
+        const u32 items = hub_steps + myblk * P2_CYC;                      // (trailing groups past NG are skipped below)
+        auto fetch = [&]() -> u32 {
+            u32 it = 0;
+            if (lane == 0) it = atomicAdd(&sm.next_group, 1u);
+            return __shfl_sync(FULL, it, 0);
+        };
+        // per-lane registers of a prefetched group
+        u64 pf_e = 0;
+        OffT pf_beg = 0;
+        double pf_r = 0.0;
+        u32 pf_i = 0;
+        bool pf_valid = false;
+        auto prefetch_group = [&](u32 it) { // it: item index >= hub_steps
+            const u32 li = it - hub_steps;
+            const u32 gj = ((li / P2_CYC) * G + c) * P2_CYC + li % P2_CYC;
+            pf_i = gj * WARP + lane;
+            pf_valid = it < items && gj < NG && pf_i < nf;
+            if (pf_valid) {
+                const int rsl = p2_slot_of(sm, k, pf_i);
+                pf_e = __ldcg(p2_front(p, a.slot0 + rsl, sm.par[rsl]) + (pf_i - sm.fbase[rsl]));
+                pf_r = __ldcg(&a.rv[pf_i]);
+                pf_beg = __ldcg(&((const OffT*)a.begs)[pf_i]);
+            }
+        };
+        u32 item = fetch();
+        if (item >= hub_steps && item < items) prefetch_group(item);
+        while (item < items) {
+            const u32 nxt = fetch();
+            if (item < hub_steps) {
+                if (nxt >= hub_steps && nxt < items) prefetch_group(nxt);
+                const u32 x0 = (hub_s0 + item) * (WARP * P2_UB);
+                p2_scatter<OffT, true>(a, g, sm, ctl, w, x0, min(EH, x0 + WARP * P2_UB), wq, wq_slot, pol_keep, pol_stream, nh);
+            } else {
+                // consume the prefetched registers, then start the next group's loads before scattering this one
+                u32 cnt = 0;
+                int rsl = 0;
+                double inc = 0.0;
+                OffT beg = 0;
+                bool dang = false;
+                if (pf_valid) {
+                    rsl = p2_slot_of(sm, k, pf_i);
+                    u32 d = entry_deg24(pf_e);
+                    if (d == DEG_SAT) d = (u32)__ldg(&p.deg[entry_vertex(pf_e)]);
+                    if (pf_r > 0.0) { // < 0: listed as a hub, handled through the hub steps
+                        dang = d == 0;
+                        beg = pf_beg;
+                        inc = dang ? pf_r * (1.0 - p.alpha) : ((1.0 - p.alpha) * pf_r) / (double)d;
+                        cnt = dang ? 1u : d;
+                    }
+                }
+                if (nxt >= hub_steps && nxt < items) prefetch_group(nxt);
+                else pf_valid = false;
+                const u32 incl = warp_incl_scan(cnt);
+                const u32 T = __shfl_sync(FULL, incl, 31);
+                sm.w_off[w][lane] = incl - cnt;
+                if (lane == 31) sm.w_off[w][32] = incl;
+                sm.w_beg32[w][lane] = (u32)(u64)beg;
+                sm.w_beghi[w][lane] = (u32)((u64)beg >> 32);
+                sm.w_inc[w][lane] = inc;
+                sm.w_slot[w][lane] = dang ? ~rsl : rsl;
+                __syncwarp();
+                if (T) p2_scatter<OffT, false>(a, g, sm, ctl, w, 0u, T, wq, wq_slot, pol_keep, pol_stream);
+                __syncwarp();
+            }
+            item = nxt;
         }
         if (wq) {
             p2_flush(a, sm, ctl, sm.wqueue[w], wq, wq_slot);
             wq = 0;
+        }
+        if (p.trace && level < p.trace_cap && c == 0) { // when CTA 0's last warp is done with phase B (before the barrier)
+            u64 t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (lane == 0) atomicMax(&p.trace[4 * level + 2], t);
         }
         grid.sync();
         if (threadIdx.x < P2_MAX_SUB) {

@@ -291,9 +291,20 @@ __host__ __device__ inline double calculate_lambda(double rsum, double pfail, do
 }
 
 // one thread per vertex of one slot; bounds start at upper = 1, lower = 0 (query.h:940-941)
-__global__ void __launch_bounds__(256) ppr_bounds_kernel(int32_t n, double rsum, double pfail, double total_rw_num,
-                                                          const double* __restrict__ ppr, const double* __restrict__ reserve,
-                                                          double* __restrict__ upper, double* __restrict__ lower) {
+// set_ppr_bounds (algo.h:1178-1261) for every listed slot in ONE launch: blockIdx.y = position in `slots`; the per-slot scalars
+// (rsum, number of walks of the round) are read from the slot block on the device, so no host round trip precedes the launch.
+// A slot takes part when delta < threshold, it walked this round and has residue left (query.h:745-746).
+__global__ void __launch_bounds__(256) ppr_bounds_kernel(int32_t n, size_t stride, const int32_t* __restrict__ slots, const double* __restrict__ rsum_of,
+                                                          const u64* __restrict__ nwalk_of, double pfail, double delta, double threshold,
+                                                          const double* __restrict__ ppr_base, const double* __restrict__ reserve_base,
+                                                          double* __restrict__ upper_base, double* __restrict__ lower_base) {
+    const int slot = slots[blockIdx.y];
+    const double rsum = rsum_of[slot], total_rw_num = (double)nwalk_of[slot];
+    if (!(delta < threshold && total_rw_num > 0 && rsum > 0)) return;
+    const double* __restrict__ ppr = ppr_base + stride * slot;
+    const double* __restrict__ reserve = reserve_base + stride * slot;
+    double* __restrict__ upper = upper_base + stride * slot;
+    double* __restrict__ lower = lower_base + stride * slot;
     const double min_ppr = 1.0 / n, sqrt_min_ppr = sqrt(1.0 / n);
     const double epsilon_v_div = sqrt(2.67 * rsum * log(2.0 / pfail) / total_rw_num);
     const double default_epsilon_v = epsilon_v_div / sqrt_min_ppr;
@@ -330,30 +341,48 @@ __global__ void fill_kernel(double* p, size_t n, double v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-// if_stop part 2 (algo.h:1124-1163) given the k nodes with the largest lower bounds:
-//   fail[0] |= any of them has upper/lower > 1+eps;   in_topk marks them
-__global__ void stop_mark_kernel(const int32_t* __restrict__ nodes, u32 k, const double* __restrict__ upper,
-                                 const double* __restrict__ lower, double eps, unsigned char* __restrict__ in_topk, u32* fail) {
+// if_stop part 2 (algo.h:1124-1163) for every listed slot in one launch each (blockIdx.y = position j in the list; vector j of the
+// preceding batched select holds the k nodes with the largest lower bounds of slot slots[j]):
+//   fail[2j]   |= any of them has upper/lower > 1+eps;   in_topk (one byte map per slot) marks them
+__global__ void stop_mark_kernel(const int32_t* __restrict__ nodes_base, u32 node_stride, u32 k, const int32_t* __restrict__ slots, size_t stride,
+                                 const double* __restrict__ upper_base, const double* __restrict__ lower_base, double eps,
+                                 unsigned char* __restrict__ in_topk_base, u32* fail) {
+    const int j = blockIdx.y, slot = slots[j];
+    const int32_t* __restrict__ nodes = nodes_base + (size_t)node_stride * j;
+    const double* __restrict__ upper = upper_base + stride * slot;
+    const double* __restrict__ lower = lower_base + stride * slot;
+    unsigned char* __restrict__ in_topk = in_topk_base + stride * slot;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) {
         const int32_t v = nodes[i];
         in_topk[v] = 1;
-        if (upper[v] / lower[v] > 1.0 + eps) atomicOr(fail, 1u);
+        if (upper[v] / lower[v] > 1.0 + eps) atomicOr(fail + 2 * j, 1u);
     }
 }
-//   fail[1] |= a node outside the top-k with ppr > 0 whose upper bound exceeds low_bound_k*(1+eps) without being
+//   fail[2j+1] |= a node outside the top-k with ppr > 0 whose upper bound exceeds low_bound_k*(1+eps) without being
 //   separated by (1+eps)/(1-eps)
-__global__ void __launch_bounds__(256) stop_tail_kernel(int32_t n, const double* __restrict__ ppr, const double* __restrict__ upper,
-                                                         const double* __restrict__ lower, const unsigned char* __restrict__ in_topk,
-                                                         double low_bound_k, double eps, u32* fail) {
+__global__ void __launch_bounds__(256) stop_tail_kernel(int32_t n, const int32_t* __restrict__ slots, size_t stride, const double* __restrict__ ppr_base,
+                                                         const double* __restrict__ upper_base, const double* __restrict__ lower_base,
+                                                         const unsigned char* __restrict__ in_topk_base, const double* __restrict__ low_bound_k_of,
+                                                         double eps, u32* fail) {
+    const int j = blockIdx.y, slot = slots[j];
+    const double* __restrict__ ppr = ppr_base + stride * slot;
+    const double* __restrict__ upper = upper_base + stride * slot;
+    const double* __restrict__ lower = lower_base + stride * slot;
+    const unsigned char* __restrict__ in_topk = in_topk_base + stride * slot;
+    const double low_bound_k = low_bound_k_of[j];
     bool bad = false;
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
         if (in_topk[v] || ppr[v] <= 0) continue;
         const double u = upper[v], l = lower[v];
         if (u > low_bound_k * (1.0 + eps) && !(u > (1 + eps) / (1 - eps) * l)) bad = true;
     }
-    if (__any_sync(FULL, bad) && lane_id() == 0) atomicOr(fail + 1, 1u);
+    if (__any_sync(FULL, bad) && lane_id() == 0) atomicOr(fail + 2 * j + 1, 1u);
 }
-__global__ void stop_unmark_kernel(const int32_t* __restrict__ nodes, u32 k, unsigned char* __restrict__ in_topk) {
+__global__ void stop_unmark_kernel(const int32_t* __restrict__ nodes_base, u32 node_stride, u32 k, const int32_t* __restrict__ slots, size_t stride,
+                                   unsigned char* __restrict__ in_topk_base) {
+    const int j = blockIdx.y;
+    const int32_t* __restrict__ nodes = nodes_base + (size_t)node_stride * j;
+    unsigned char* __restrict__ in_topk = in_topk_base + stride * slots[j];
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < k; i += gridDim.x * blockDim.x) in_topk[nodes[i]] = 0;
 }
 

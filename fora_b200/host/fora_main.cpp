@@ -42,6 +42,7 @@ struct Config {
     unsigned query_size = 1000, k = 500, hub_space_consum = 1;
     int gpus = 1, slots = 16;
     uint64_t seed = 0;
+    bool split = false; // --split: the GPUs of --gpus answer every query TOGETHER (whole-graph SSPPR on huge graphs)
     string get_graph_folder() const { return prefix + graph_alias + "/"; }
 };
 static Config config;
@@ -137,17 +138,25 @@ static string exact_topk_file() { // build.h:121-125
 struct Gpu {
     fora_ctx* ctx = nullptr;
 };
+static fora_group* g_group = nullptr; // --split: the contexts belong to one NCCL group
 static vector<Gpu> open_gpus(const GraphHost& g, bool need_in) {
     vector<Gpu> gp((size_t)config.gpus);
     const uint64_t seed = config.seed ? config.seed : (uint64_t)time(nullptr); // the reference seeds from time(0)
+    if (config.split && fora_group_create(config.gpus, nullptr, seed, &g_group)) die(string("fora_b200: ") + fora_group_last_error(nullptr));
     for (int d = 0; d < config.gpus; ++d) {
-        if (fora_ctx_create(d, seed, &gp[d].ctx)) die(string("fora_b200: ") + fora_last_error(nullptr));
-        CKF(gp[d].ctx, fora_ctx_set_slots(gp[d].ctx, config.slots));
+        if (g_group) gp[d].ctx = fora_group_ctx(g_group, d);
+        else if (fora_ctx_create(d, seed, &gp[d].ctx)) die(string("fora_b200: ") + fora_last_error(nullptr));
+        CKF(gp[d].ctx, fora_ctx_set_slots(gp[d].ctx, g_group ? 1 : config.slots));
         CKF(gp[d].ctx, fora_graph_build_from_edges(gp[d].ctx, g.n, g.m, g.src.data(), g.dst.data(), (int64_t)g.src.size(), need_in ? 1 : 0));
     }
     return gp;
 }
 static void close_gpus(vector<Gpu>& gp) {
+    if (g_group) {
+        fora_group_destroy(g_group);
+        g_group = nullptr;
+        return;
+    }
     for (auto& x : gp) fora_ctx_destroy(x.ctx);
 }
 static void set_params_all(vector<Gpu>& gp) {
@@ -303,6 +312,30 @@ static Result do_query(const GraphHost& g, vector<Gpu>& gp) { // query(), query.
     vector<int32_t> src(queries.begin(), queries.begin() + query_size);
     vector<fora_query_stat> stats(query_size);
     vector<fora_batch_timing> tms(gp.size());
+    if (g_group) { // --split: one query at a time, all GPUs on it (push on GPU 0, NCCL broadcast, walks split, NCCL all-reduce)
+        if (config.algo != "fora") die("--split applies to --algo fora");
+        Result r;
+        const double t0s = wall();
+        double bc = 0, rd = 0;
+        for (unsigned i = 0; i < query_size; ++i) {
+            fora_split_timing st;
+            if (fora_group_query_split(g_group, src[i], i, nullptr, &stats[i], &st)) die(string("fora_b200: ") + fora_group_last_error(g_group));
+            cout << i + 1 << ". source node:" << src[i] << endl;
+            cout << "  split over " << st.n_gpus << " GPU(s): total " << st.total_ms << " ms = push " << st.push_ms << " + broadcast " << st.bcast_ms << " ("
+                 << st.bcast_bytes << " B) + walks " << st.walk_ms << " + all-reduce " << st.reduce_ms << " (" << st.reduce_bytes << " B)" << endl;
+            r.num_randwalk += (double)stats[i].n_walks;
+            r.push_time += st.push_ms / 1e3;
+            r.rw_time += st.walk_ms / 1e3;
+            bc += st.bcast_ms / 1e3;
+            rd += st.reduce_ms / 1e3;
+        }
+        r.total_time = wall() - t0s;
+        r.avg_query_time = r.total_time / query_size;
+        cout << "NCCL broadcast " << bc << " s, all-reduce " << rd << " s in total" << endl;
+        config.query_size = query_size;
+        display_time_usage(r, query_size);
+        return r;
+    }
     auto sh = shards((int)query_size, (int)gp.size());
     const double t0 = wall();
     vector<thread> th;
@@ -491,6 +524,14 @@ static void do_build(const GraphHost& g, vector<Gpu>& gp) { // build(), build.h:
         });
     for (auto& t : th) t.join();
     cout << "index walks generated in " << wall() - t0 << " s on " << gp.size() << " GPU(s)" << endl;
+    for (size_t d = 0; d < gp.size(); ++d) {
+        uint64_t w = 0, hp = 0;
+        double ms = 0;
+        fora_index_build_stat(gp[d].ctx, &w, &hp, &ms);
+        if (w) // index build moves 20 B per hop + 4 B per destination
+            cout << "  GPU " << d << ": " << w << " walks, " << hp << " hops, walk kernels " << ms << " ms = " << hp / ms / 1e6 << " G hops/s, "
+                 << (20.0 * hp + 4.0 * w) / ms / 1e6 << " GB/s algorithmic" << endl;
+    }
     cout << "materializing..." << endl << "rw_idx.size()=" << dest.size() << " rw_idx_info.size()=" << off.size() << endl;
     try {
         save_index_dest(idx_name("idx"), dest);
@@ -552,7 +593,7 @@ int main(int argc, char* argv[]) {
                     "fora build [options]\nfora generate-ss-query [options]\nfora gen-exact-topk [options]\nfora\n\nalgo: \n  bippr\n  montecarlo\n  fora\n  fwdpush\n"
                     "options: \n  --prefix <prefix>\n  --epsilon <epsilon>\n  --dataset <dataset>\n  --query_size <queries count>\n  --k <top k>\n  --with_idx\n"
                     "  --exact_ppr_path <eaact-topk-pprs-path>\n  --rw_ratio <rand-walk cost ratio>\n  --result_dir <directory to place results>  --rmax_scale <scale of rmax>\n"
-                    "  --opt\n  --balanced\n  --gpus <number of GPUs>\n  --seed <rng seed>\n  --slots <concurrent queries per GPU>\n"
+                    "  --opt\n  --balanced\n  --gpus <number of GPUs>\n  --split (all GPUs on one query at a time)\n  --seed <rng seed>\n  --slots <concurrent queries per GPU>\n"
                  << endl;
             exit(0);
         }
@@ -580,6 +621,7 @@ int main(int argc, char* argv[]) {
         else if (arg == "--opt") config.opt = true;
         else if (arg == "--balanced") config.balanced = true;
         else if (arg == "--gpus") config.gpus = max(1, atoi(val(i + 1)));
+        else if (arg == "--split") config.split = true;
         else if (arg == "--seed") config.seed = strtoull(val(i + 1), nullptr, 10);
         else if (arg == "--slots") config.slots = max(1, atoi(val(i + 1)));
         else if (arg.substr(0, 2) == "--") {

@@ -191,6 +191,26 @@ int fora_device_to_original(fora_ctx* ctx, const double* d_internal, double* d_o
 int fora_compute_ppr_part_device(fora_ctx* ctx, double rsum, uint32_t query_id, uint32_t part, uint32_t nparts,
                                  fora_query_stat* stat); /* result in fora_device_reserve(ctx, 0) */
 
+/* ---- the same split inside ONE process: a group of GPUs, NCCL collectives issued by the library (loaded at run time) ----
+ * fora_group_create opens one context per GPU (same seed) and one NCCL communicator per GPU; upload the graph and set the
+ * parameters on every fora_group_ctx(g, i).  fora_group_query_split then answers ONE whole-graph query with all GPUs: GPU 0
+ * pushes (forward_local_update_linear_topk rounds of fora_query_basic, query.h:848-884 -- with G GPUs a walk costs 1/G, so
+ * --balanced stops the push earlier), the compacted (vertex, residue) list is broadcast (ncclBroadcast), every GPU walks chunk
+ * range g of G of the same walk plan (compute_ppr_with_fwdidx{,_opt}, query.h:255-413), one ncclAllReduce sums the dense
+ * vectors.  ppr: host double[n] (original ids) or NULL.  The result equals the single-GPU result up to fp64 summation order. */
+typedef struct fora_group fora_group;
+typedef struct fora_split_timing { /* GPU milliseconds (CUDA events); walk_ms = slowest GPU */
+    float total_ms, push_ms, bcast_ms, walk_ms, reduce_ms;
+    uint32_t n_gpus;
+    uint64_t bcast_bytes, reduce_bytes;
+} fora_split_timing;
+int fora_group_create(int n_gpus, const int* devices /* NULL: 0..n_gpus-1 */, uint64_t seed, fora_group** out);
+void fora_group_destroy(fora_group* g);
+int fora_group_size(fora_group* g);
+fora_ctx* fora_group_ctx(fora_group* g, int i);
+const char* fora_group_last_error(fora_group* g); /* g may be NULL: last creation error */
+int fora_group_query_split(fora_group* g, int32_t source, uint32_t query_id, double* ppr, fora_query_stat* stat, fora_split_timing* timing);
+
 /* get_topk(), query.h:1139-1190: k (node,value) pairs per query, descending, unfilled = (0,0.0)
  * (algo.h:592-610).  iters: per-query refinement rounds (num_iter_topk) or NULL. */
 int fora_topk_batch(fora_ctx* ctx, int algo, const int32_t* sources, int32_t n_q, uint32_t k, int32_t* nodes,

@@ -80,6 +80,7 @@ for spec in args or ["default={}"]:
             t = out[: 4 * lvn].reshape(lvn, 4).astype(np.int64)
             for i in range(lvn - 1):
                 dt = t[i + 1, 0] - t[i, 0]
-                print("  L%3d nf=%8d  level %8.1f us  phaseA %7.1f us" % (i, t[i, 1], dt / 1e3, (t[i, 3] - t[i, 0]) / 1e3))
+                print("  L%3d nf=%8d  level %8.1f us  phaseA+barrier %7.1f us  CTA0 phase B %7.1f us  wait at level barrier %7.1f us" % (
+                    i, t[i, 1], dt / 1e3, (t[i, 3] - t[i, 0]) / 1e3, (t[i, 2] - t[i, 3]) / 1e3, (t[i + 1, 0] - t[i, 2]) / 1e3))
     finally:
         E.close()

@@ -40,6 +40,16 @@ if "topk" in which:
         *_, st, tm = E.topk_batch(algo, q[nq:2 * nq], 500)
         show(name, nq, tm)
     E.close()
+if "mc" in which:  # Monte-Carlo baseline (query.h:16-43) and BiPPR's walk phase run through the chunked walk kernel
+    n, E = eng("lj")
+    q = np.random.default_rng(43).integers(0, n, 1000).astype(np.int32)
+    rmax, omega = E.configure("montecarlo", 0.5)
+    E.query_batch("montecarlo", q[:1], want_ppr=False)
+    _, st, tm = E.query_batch("montecarlo", q[1:5], want_ppr=False)
+    hops = sum(s["walk_hops"] for s in st)
+    print("lj montecarlo %.1f ms/query, walk kernels %.1f ms/query: %.1f G hops/s (%.3g walks per query)" % (
+        tm["total_ms"] / 4, tm["walk_kernel_ms"] / 4, hops / tm["walk_kernel_ms"] / 1e6, st[0]["n_walks"]), flush=True)
+    E.close()
 if "pokec" in which:
     n, E = eng("pokec")
     q = np.random.default_rng(43).integers(0, n, 1000).astype(np.int32)
@@ -47,7 +57,10 @@ if "pokec" in which:
     off, cnt, total = E.index_info()
     E.index_build(off, cnt)
     t = time.perf_counter(); dest = E.index_build(off, cnt); dt = time.perf_counter() - t
-    print("pokec index build %.1f ms wall (%d entries, incl. D2H of the index)" % (dt * 1e3, total), flush=True)
+    walks, hops, kms = E.index_build_stat()
+    # index build bytes = 20*hops + 4*walks
+    print("pokec index build %.1f ms wall (%d entries, incl. D2H of the index into pageable memory) | walk kernels %.2f ms: %.1f G hops/s, %.0f GB/s algorithmic (20*hops+4*walks)" % (
+        dt * 1e3, total, kms, hops / kms / 1e6, (20.0 * hops + 4.0 * walks) / kms / 1e6), flush=True)
     E.index_upload(off, cnt, dest)
     E.query_batch("fora", q[:32], want_ppr=False)
     _, st, tm = E.query_batch("fora", q[32:160], want_ppr=False)
