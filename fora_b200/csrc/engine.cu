@@ -158,8 +158,6 @@ struct fora_ctx {
     int push_grid = 0;
     // second-generation push (push2.cuh): sub-waves of push_sub slots, tails per slot
     int push_v = 1, push_sub = 2, push2_grid = 0, push_prefetch = 1;
-    u32 push_hot = 0;          // vertices per slot whose residue atomics carry evict_last (0: all of them)
-    u32 push_cold_policy = 0;
     size_t persist_now = (size_t)-1, persist_walk = 0; // current persisting carve-out / the one the walk phase wants
     int push_win = 1;          // pin the sub-wave's residue vectors with an access-policy window (persisting L2 lines)
     int push_win_reset = 0;    // cudaCtxResetPersistingL2Cache after the push phase
@@ -841,9 +839,6 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
                 ctx->push_carve = std::min(ctx->push_carve, ctx->l2_persist_max);
             }
             ctx->persist_walk = limit;
-            ctx->push_hot = getenv("FORA_PUSH_HOT") ? (u32)atol(getenv("FORA_PUSH_HOT")) : 0u;
-            ctx->push_cold_policy = getenv("FORA_PUSH_COLD") ? (u32)atoi(getenv("FORA_PUSH_COLD")) : 0u;
-            if (ctx->push_hot && !fits && !ctx->push_carve) ctx->push_carve = ctx->l2_persist_max;
             if (fits) { ctx->push_carve = 0; limit = ctx->l2_persist_max; ctx->persist_walk = limit; }
             int lrc = set_persist_limit(ctx, ctx->persist_walk);
             if (lrc) return lrc;
@@ -996,6 +991,7 @@ static int meta_d2h_sync(fora_ctx* ctx) {
     CKL();
     CK(cudaStreamSynchronize(ctx->stream));
     kev_harvest(ctx);
+    if (ctx->h_meta->push_err) return ctx->fail(FORA_ECUDA, "push: level cap reached with a non-empty frontier");
     return FORA_OK;
 }
 
@@ -1033,8 +1029,7 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     a.log_cur = ctx->log_cur.p;
     a.colx = ctx->g.deg_shift ? ctx->g.out_colx : nullptr;
     a.deg_shift = ctx->g.deg_shift;
-    a.hot_limit = ctx->push_hot;
-    a.cold_policy = ctx->push_cold_policy;
+    a.err = &m->push_err;
     return a;
 }
 
@@ -1615,6 +1610,14 @@ extern "C" int fora_compute_ppr(fora_ctx* ctx, const double* reserve, const doub
     if (rc) return rc;
     if (!reserve || !residue || !ppr) return ctx->fail(FORA_EINVAL, "null vector");
     const size_t n = (size_t)ctx->g.n;
+    { // the walk plan is sized from omega*rsum + n walks: rsum must be the sum of the residues (query.h:255-270 takes it from the push)
+        double sum = 0.0;
+        for (size_t i = 0; i < n; ++i) {
+            if (!(residue[i] >= 0.0)) return ctx->fail(FORA_EINVAL, "compute_ppr: negative or NaN residue");
+            sum += residue[i];
+        }
+        if (!(rsum >= 0.0 && rsum <= 1.0 + 1e-9) || fabs(sum - rsum) > 1e-9 * std::max(1.0, rsum)) return ctx->fail(FORA_EINVAL, "compute_ppr: rsum is not the sum of the residue vector");
+    }
     SlotMeta* h = ctx->h_meta;
     memset(h, 0, sizeof *h);
     for (int s = 0; s < MAX_SLOTS; ++s) h->source[s] = -1;

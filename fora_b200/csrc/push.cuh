@@ -94,11 +94,7 @@ struct PushArgs {
     u32 l2_hints;                        // 1: evict_last on residue atomics / degree loads, evict_first on streams
     const int32_t* __restrict__ colx;    // optional packed columns: id | min(d_out(id), dmax) << deg_shift (null: plain g.col)
     u32 deg_shift;                       // id bits of a packed column entry; the remaining high bits hold the out-degree code
-    // selective L2 residency: vertices are numbered hot-first (relabelling by in-degree), so the first hot_limit entries of every
-    // slot's residue vector take most scatters.  Their atomics carry evict_last (the persisting carve-out holds them across
-    // levels although the wave's vectors are 15x the L2), the rest cold_policy (0 normal, 1 evict_first).  0: hint everything.
-    u32 hot_limit;
-    u32 cold_policy;
+    int32_t* err;                        // [1] set when the level cap stops a launch with a non-empty frontier
     // reserve credit log: phase A appends (vertex, residue pushed) instead of the random read-modify-write of reserve[v];
     // apply_log_kernel adds alpha*r slot by slot later (engine.cu).  Entries that do not fit take the direct update.
     int32_t* log_v;                      // [slots*log_cap], null: no log
@@ -140,16 +136,6 @@ __device__ __forceinline__ u64 l2_policy_evict_first() {
     u64 p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
-}
-__device__ __forceinline__ u64 l2_policy_evict_normal() {
-    u64 p;
-    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ u64 atomic_exch_u64_hint(u64* addr, u64 v, u64 policy) {
-    u64 old;
-    asm volatile("atom.global.exch.L2::cache_hint.b64 %0, [%1], %2, %3;" : "=l"(old) : "l"(addr), "l"(v), "l"(policy) : "memory");
-    return old;
 }
 __device__ __forceinline__ double atomic_add_f64_hint(double* addr, double v, u64 policy) {
     double old;
@@ -206,7 +192,6 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
     const int lane = lane_id();
     const u32 cs = (nf + count - 1) / count;
     const u32 lo_i = min(nf, rank * cs), hi_i = min(nf, lo_i + cs);
-    const u64 pol_hot = l2_policy_evict_last(), pol_cold = a.cold_policy ? l2_policy_evict_first() : l2_policy_evict_normal();
     u64 carry = 0;
     int parity = 0;
     for (u32 b0 = lo_i; b0 < hi_i; b0 += PUSH_THREADS * PUSH_UA) {
@@ -227,8 +212,7 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
                 // the store right behind the load, it reaches the L2 while the sector's fill is still pending and takes a slow
                 // path -- phase A ran 3x slower.  Ordering the store behind the load by a data dependency fixed that; the
                 // exchange is 1.4 % faster still.)
-                if (a.hot_limit) r[k] = __longlong_as_double((long long)atomic_exch_u64_hint((u64*)&a.residue[gi], 0ull, (u32)e[k] < a.hot_limit ? pol_hot : pol_cold));
-                else r[k] = __longlong_as_double((long long)atomicExch((unsigned long long*)&a.residue[gi], 0ull));
+                r[k] = __longlong_as_double((long long)atomicExch((unsigned long long*)&a.residue[gi], 0ull));
                 lp[k] = sm.logbase[slot] + (i0 + k - sm.fbase[slot]);
                 if (!(a.log_v && lp[k] < a.log_cap)) {
                     lp[k] = 0xffffffffu; // no room (or no log): direct update of the reserve
@@ -351,7 +335,6 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
     u64 T = (E + count - 1) / count;
     T = T < TILE_MIN ? TILE_MIN : (T > a.tile_max ? a.tile_max : T);
     const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
-    const u64 pol_cold = a.cold_policy ? pol_stream : l2_policy_evict_normal();
     u32 wq = 0;       // entries in this warp's queue (warp-uniform register)
     int wq_slot = 0;  // the slot they belong to
     u64* myq = sm.wqueue[w];
@@ -463,7 +446,7 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
                     du[k] = 0;
                     if (ok[k]) {
                         double* rp = &a.residue[(size_t)slot[k] * a.n + u[k]];
-                        old[k] = a.l2_hints ? atomic_add_f64_hint(rp, inc[k], (a.hot_limit && (u32)u[k] >= a.hot_limit) ? pol_cold : pol_keep) : atomicAdd(rp, inc[k]);
+                        old[k] = a.l2_hints ? atomic_add_f64_hint(rp, inc[k], pol_keep) : atomicAdd(rp, inc[k]);
                         if (dcode[k] != dmax) du[k] = (int32_t)dcode[k];
                         else du[k] = a.l2_hints ? ld_s32_hint(&a.deg[u[k]], pol_keep) : __ldg(&a.deg[u[k]]);
                     }
@@ -534,7 +517,13 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         }
         __syncthreads();
         const u32 nf = sm.fbase[a.slots];
-        if (nf == 0 || level >= a.max_levels) break;
+        if (nf == 0) break;
+        if (level >= a.max_levels) { // never reached in practice (2^20 levels): report instead of dropping the frontier silently
+            if (blockIdx.x == 0 && threadIdx.x == 0 && a.err) *a.err = 1;
+            if (threadIdx.x < (u32)a.slots) sm.prevcnt[threadIdx.x] = 0; // the counts just read belong to a level that did not run: not logged
+            __syncthreads();
+            break;
+        }
         const u64* cur = (level & 1) ? a.front1 : a.front0; // written by the previous level: L2 reads only
         u64* nxt = (level & 1) ? a.front0 : a.front1;
         u32* nxt_count = ctl->fcount[(level + 1) % 3];

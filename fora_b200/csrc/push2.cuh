@@ -130,7 +130,6 @@ __device__ __forceinline__ void p2_scatter(const Push2Args& a, const CsrView<Off
     const PushArgs& p = a.p;
     const int lane = lane_id();
     u64* myq = sm.wqueue[w];
-    const u64 pol_cold = p.cold_policy ? pol_stream : l2_policy_evict_normal();
     const u32* off = WIDE ? sm.hb_off : sm.w_off[w];
     const u32* beg32 = WIDE ? sm.hb_beg32 : sm.w_beg32[w];
     const u32* beghi = WIDE ? sm.hb_beghi : sm.w_beghi[w];
@@ -189,7 +188,7 @@ __device__ __forceinline__ void p2_scatter(const Push2Args& a, const CsrView<Off
             du[k] = 0;
             if (ok[k]) {
                 double* rp = &p.residue[(size_t)(a.slot0 + rs[k]) * p.n + u[k]];
-                old[k] = p.l2_hints ? atomic_add_f64_hint(rp, inc[k], (p.hot_limit && (u32)u[k] >= p.hot_limit) ? pol_cold : pol_keep) : atomicAdd(rp, inc[k]);
+                old[k] = p.l2_hints ? atomic_add_f64_hint(rp, inc[k], pol_keep) : atomicAdd(rp, inc[k]);
                 if (dcode[k] != dmax) du[k] = (int32_t)dcode[k];
                 else du[k] = p.l2_hints ? ld_s32_hint(&p.deg[u[k]], pol_keep) : __ldg(&p.deg[u[k]]);
             }
