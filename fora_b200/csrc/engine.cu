@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "push.cuh"
 #include "push2.cuh"
+#include "push3.cuh"
 #include "topk.cuh"
 #include "walk.cuh"
 
@@ -165,6 +166,14 @@ struct fora_ctx {
     u32 tail_nf = 1024, tail_e = 8192;
     DevBuf<u32> hubbuf;
     DevBuf<u64> front_begs;
+    // third-generation push (push3.cuh): lockstep sweep over slot groups
+    int push3_grid = 0;
+    DevBuf<P3Ctl> p3ctl;
+    DevBuf<u64> p3hub;
+    size_t p3hub_cap = 0;
+    double p3_budget = 1.0; // a group's estimated scatter footprint, in residue vectors
+    u32 p3_hub_deg = P3_HUB_DEG, p3_hub_piece = P3_HUB_PIECE;
+    double p3_dense = 1.0 / 32;
     // bulk walks (index build / Monte-Carlo / BiPPR) through the chunked walk kernel
     DevBuf<u32> bulk_chunk_first;
     DevBuf<unsigned char> bulk_meta;
@@ -904,6 +913,39 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         }
         if (per_sm2 < 1) return ctx->fail(FORA_ECUDA, "push2 kernel does not fit on an SM");
         ctx->push2_grid = ctx->num_sms; // one CTA per SM: the grid barrier has 148 participants
+        // third-generation push: hub piece lists (3 rotating sets; a slot-level lists every vertex at most once, so
+        // sum ceil(d/1024) over vertices with d > 2048 bounds a slot's pieces)
+        {
+            if (getenv("FORA_P3_HUB")) { // test hook: "deg,piece" (small values exercise the piece path on small graphs)
+                unsigned hd = 0, hp = 0;
+                if (sscanf(getenv("FORA_P3_HUB"), "%u,%u", &hd, &hp) == 2 && hd >= 1 && hp >= 1) { ctx->p3_hub_deg = hd; ctx->p3_hub_piece = hp; }
+            }
+            // exact bound of a slot-level's piece list: every vertex is in a frontier at most once per level
+            CK(ctx->scratch64.ensure(1));
+            CK(cudaMemsetAsync(ctx->scratch64.p, 0, sizeof(u64), ctx->stream));
+            hub_pieces_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(g.n, ctx->hot_deg, ctx->p3_hub_deg, ctx->p3_hub_piece, ctx->scratch64.p);
+            CKL();
+            u64 pieces = 0;
+            CK(cudaMemcpyAsync(&pieces, ctx->scratch64.p, sizeof(u64), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            ctx->p3hub_cap = std::min<size_t>((size_t)pieces + 16, 0xfffffff0u);
+            CK(ctx->p3hub.ensure(2 * (size_t)S * ctx->p3hub_cap));
+            CK(ctx->p3ctl.ensure(1));
+            ctx->p3_budget = getenv("FORA_P3_BUDGET") ? atof(getenv("FORA_P3_BUDGET")) : 1.0;
+            // a slot-level with at least this fraction of the vertices in its frontier runs in dense mode (RED + scan); < 0: never
+            ctx->p3_dense = getenv("FORA_P3_DENSE") ? atof(getenv("FORA_P3_DENSE")) : 1.0 / 32;
+            int per_sm3 = 0;
+            if (g.off32) {
+                CK(cudaFuncSetAttribute(push3_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P3Smem)));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, push3_kernel<u32>, P3_THREADS, sizeof(P3Smem)));
+            } else {
+                CK(cudaFuncSetAttribute(push3_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(P3Smem)));
+                CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm3, push3_kernel<int64_t>, P3_THREADS, sizeof(P3Smem)));
+            }
+            if (per_sm3 < 1) return ctx->fail(FORA_ECUDA, "push3 kernel does not fit on an SM");
+            const int want = getenv("FORA_P3_CTAS") ? atoi(getenv("FORA_P3_CTAS")) : 2;
+            ctx->push3_grid = std::min(std::min(per_sm3, std::max(1, want)) * ctx->num_sms, MAX_PUSH_CTAS);
+        }
     }
     // walks per slot <= omega*rsum + #sources <= omega + n
     const size_t need = std::max((size_t)WALK_TARGET_CHUNKS + 1, (size_t)((omega_max + (double)n) / WALK_CHUNK)) + 4; // see walk_chunk_size
@@ -1046,8 +1088,10 @@ static int apply_push_log(fora_ctx* ctx) {
 // launch the persistent push kernel over whatever frontier is in front0 / ctl->fcount[0].  defer_log: leave the reserve
 // credits of this launch in the log (the caller applies them once after the last round of the wave).
 static int launch_push2(fora_ctx* ctx, bool defer_log);
+static int launch_push3(fora_ctx* ctx, bool defer_log);
 static int launch_push(fora_ctx* ctx, bool defer_log = false) {
     if (ctx->push_v == 2) return launch_push2(ctx, defer_log);
+    if (ctx->push_v == 3) return launch_push3(ctx, defer_log);
     PushArgs a = make_push_args(ctx);
     ctx->level_base += (1u << 20);
     int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
@@ -1062,6 +1106,39 @@ static int launch_push(fora_ctx* ctx, bool defer_log = false) {
         CsrView<int64_t> v{ctx->g.out_ptr64, ctx->g.out_col};
         void* args[] = {&a, &v};
         CK(cudaLaunchCooperativeKernel((void*)push_kernel<int64_t>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, sizeof(PushSmem<int64_t>), ctx->stream));
+    }
+    kev_end(ctx);
+    ctx->launches++;
+    return defer_log ? FORA_OK : apply_push_log(ctx);
+}
+
+// Third-generation push (push3.cuh): the same persistent cooperative launch as launch_push, the grid sweeps the slots in lockstep.
+static int launch_push3(fora_ctx* ctx, bool defer_log) {
+    PushArgs a = make_push_args(ctx);
+    P3Args x{};
+    x.c = ctx->p3ctl.p;
+    x.hub_list = ctx->p3hub.p;
+    x.hub_cap = (u32)ctx->p3hub_cap;
+    x.est_deg = (u32)std::max<int64_t>(1, (ctx->g.n_edges + ctx->g.n - 1) / std::max(1, ctx->g.n));
+    x.budget_sectors = (u32)std::min<double>(4.0e9, std::max(1.0, ctx->p3_budget * (double)ctx->g.n / 4.0));
+    x.beg32 = ctx->eoff.p;
+    x.hub_deg = ctx->p3_hub_deg;
+    x.debug_mode = getenv("FORA_DEBUG_P3_MODE") ? (u32)atoi(getenv("FORA_DEBUG_P3_MODE")) : 0u;
+    x.debug_skip_hot = getenv("FORA_DEBUG_P3_SKIPHOT") ? (u32)atoi(getenv("FORA_DEBUG_P3_SKIPHOT")) : 0u;
+    x.dense_min = ctx->p3_dense < 0 ? 0xffffffffu : (u32)std::max(1.0, ctx->p3_dense * (double)ctx->g.n);
+    x.hub_piece = ctx->p3_hub_piece;
+    ctx->level_base += (1u << 20);
+    int wrc = set_l2_window(ctx, ctx->win_push_off, ctx->win_push_bytes);
+    if (wrc) return wrc;
+    kev_begin(ctx, 0);
+    if (ctx->g.off32) {
+        CsrView<u32> v{ctx->hot_ptr32, ctx->g.out_col};
+        void* args[] = {&a, &v, &x};
+        CK(cudaLaunchCooperativeKernel((void*)push3_kernel<u32>, dim3(ctx->push3_grid), dim3(P3_THREADS), args, sizeof(P3Smem), ctx->stream));
+    } else {
+        CsrView<int64_t> v{ctx->g.out_ptr64, ctx->g.out_col};
+        void* args[] = {&a, &v, &x};
+        CK(cudaLaunchCooperativeKernel((void*)push3_kernel<int64_t>, dim3(ctx->push3_grid), dim3(P3_THREADS), args, sizeof(P3Smem), ctx->stream));
     }
     kev_end(ctx);
     ctx->launches++;
@@ -2526,7 +2603,7 @@ extern "C" int fora_debug_push_trace(fora_ctx* ctx, uint64_t* out, int cap_level
     PushCtl h;
     cudaMemcpy(&h, ctx->ctl.p, sizeof h, cudaMemcpyDeviceToHost);
     const int lv = std::min<int>({(int)h.levels_run, cap_levels, 4096});
-    cudaMemcpy(out, ctx->trace.p, sizeof(u64) * 4 * lv, cudaMemcpyDeviceToHost);
+    cudaMemcpy(out, ctx->trace.p, sizeof(u64) * 4 * std::min(cap_levels, 4096), cudaMemcpyDeviceToHost); // (push3 keeps more behind the levels)
     return lv;
 }
 

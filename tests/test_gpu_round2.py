@@ -196,7 +196,13 @@ print("RESULT" + json.dumps(out))
     base = run({"FORA_PUSH_V": "1"})
     for env in ({"FORA_PUSH_V": "2", "FORA_PUSH_SUB": "2"}, {"FORA_PUSH_V": "2", "FORA_PUSH_SUB": "3", "FORA_TAIL_NF": "64", "FORA_TAIL_E": "300"},
                 {"FORA_PUSH_V": "2", "FORA_PUSH_SUB": "1", "FORA_TAIL_NF": "2048", "FORA_TAIL_E": "100000"},
-                {"FORA_PUSH_V": "2", "FORA_PUSH_SUB": "8", "FORA_TAIL_NF": "0", "FORA_PUSH_PREFETCH": "0"}):
+                {"FORA_PUSH_V": "2", "FORA_PUSH_SUB": "8", "FORA_TAIL_NF": "0", "FORA_PUSH_PREFETCH": "0"},
+                # lockstep kernel (push3.cuh): one group per level, one slot per group, hubs cut into small pieces, plain atomics
+                # (push3.cuh) default thresholds; every slot-level dense (RED + scan); never dense with tiny groups; hubs cut into
+                # small pieces in both modes; plain atomics and no credit log
+                {"FORA_PUSH_V": "3"}, {"FORA_PUSH_V": "3", "FORA_P3_DENSE": "0"}, {"FORA_PUSH_V": "3", "FORA_P3_DENSE": "-1", "FORA_P3_BUDGET": "0.002"},
+                {"FORA_PUSH_V": "3", "FORA_P3_DENSE": "0.01", "FORA_P3_BUDGET": "0.05", "FORA_P3_HUB": "40,16"},
+                {"FORA_PUSH_V": "3", "FORA_P3_DENSE": "0.001", "FORA_P3_BUDGET": "0.0001", "FORA_P3_HUB": "1,1", "FORA_L2_HINTS": "0", "FORA_PUSH_LOG": "0"}):
         got = run(env)
         assert got["push"][3:] == base["push"][3:], env
         assert relerr(np.array(got["push"][0]), np.array(base["push"][0])) < 1e-9 and relerr(np.array(got["push"][1]), np.array(base["push"][1])) < 1e-9
