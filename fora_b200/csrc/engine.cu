@@ -885,11 +885,13 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         // occupancy-sized cooperative grid
         int per_sm = 0;
         if (g.off32) {
-            CK(cudaFuncSetAttribute(push_kernel<u32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<u32>)));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<u32>, PUSH_THREADS, sizeof(PushSmem<u32>)));
+            CK(cudaFuncSetAttribute(push_kernel<u32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<u32>)));
+            CK(cudaFuncSetAttribute(push_kernel<u32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<u32>)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<u32, true>, PUSH_THREADS, sizeof(PushSmem<u32>)));
         } else {
-            CK(cudaFuncSetAttribute(push_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<int64_t>)));
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<int64_t>, PUSH_THREADS, sizeof(PushSmem<int64_t>)));
+            CK(cudaFuncSetAttribute(push_kernel<int64_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<int64_t>)));
+            CK(cudaFuncSetAttribute(push_kernel<int64_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PushSmem<int64_t>)));
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, push_kernel<int64_t, true>, PUSH_THREADS, sizeof(PushSmem<int64_t>)));
         }
         if (per_sm < 1) return ctx->fail(FORA_ECUDA, "push kernel does not fit on an SM");
         ctx->push_grid = std::min(per_sm * ctx->num_sms, MAX_PUSH_CTAS);
@@ -1072,6 +1074,11 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     a.colx = ctx->g.deg_shift ? ctx->g.out_colx : nullptr;
     a.deg_shift = ctx->g.deg_shift;
     a.err = &m->push_err;
+    // dense slot-levels (RED + scan): frontier size, as a fraction of the vertices, from which a slot-level takes that path; < 0: never
+    {
+        const double f = getenv("FORA_PUSH_DENSE") ? atof(getenv("FORA_PUSH_DENSE")) : -1.0;
+        a.dense_min = f < 0 ? 0xffffffffu : (u32)std::max(1.0, f * (double)ctx->g.n);
+    }
     return a;
 }
 
@@ -1101,11 +1108,13 @@ static int launch_push(fora_ctx* ctx, bool defer_log = false) {
     if (ctx->g.off32) {
         CsrView<u32> v{ctx->hot_ptr32, ctx->g.out_col};
         void* args[] = {&a, &v};
-        CK(cudaLaunchCooperativeKernel((void*)push_kernel<u32>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, sizeof(PushSmem<u32>), ctx->stream));
+        CK(cudaLaunchCooperativeKernel(a.dense_min != 0xffffffffu ? (void*)push_kernel<u32, true> : (void*)push_kernel<u32, false>, dim3(ctx->push_grid),
+                                       dim3(PUSH_THREADS), args, sizeof(PushSmem<u32>), ctx->stream));
     } else {
         CsrView<int64_t> v{ctx->g.out_ptr64, ctx->g.out_col};
         void* args[] = {&a, &v};
-        CK(cudaLaunchCooperativeKernel((void*)push_kernel<int64_t>, dim3(ctx->push_grid), dim3(PUSH_THREADS), args, sizeof(PushSmem<int64_t>), ctx->stream));
+        CK(cudaLaunchCooperativeKernel(a.dense_min != 0xffffffffu ? (void*)push_kernel<int64_t, true> : (void*)push_kernel<int64_t, false>, dim3(ctx->push_grid),
+                                       dim3(PUSH_THREADS), args, sizeof(PushSmem<int64_t>), ctx->stream));
     }
     kev_end(ctx);
     ctx->launches++;

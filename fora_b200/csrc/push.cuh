@@ -48,6 +48,7 @@ constexpr int PUSH_UB = CFG_PUSH_UB;       // edges in flight per lane in phase 
 #define CFG_PUSH_WQ 256
 #endif
 constexpr int PUSH_WQ = CFG_PUSH_WQ;     // per-warp queue of crossing vertices
+constexpr int SCAN_K = 8;                // dense scan: vertices per thread and tile (tile = 8 * 512 vertices)
 
 // frontier entry: [slot:8][min(out-degree, 2^24-1):24][vertex:32].  Whoever appends a vertex has just loaded its
 // out-degree for the threshold test, so carrying it saves phase A one random access per vertex.
@@ -101,6 +102,9 @@ struct PushArgs {
     double* log_r;                       // [slots*log_cap]
     u32 log_cap;
     u32* log_cur;                        // [MAX_SLOTS] entries logged so far in this wave, per slot
+    // dense slot-levels: a slot whose frontier has at least dense_min entries scatters with RED (no return value) and its next
+    // frontier is found by one scan of its residue vector, which also does that frontier's phase A (0xffffffff: never)
+    u32 dense_min;
 };
 
 // dynamic shared memory of the push kernel (~70 KB, two CTAs per SM)
@@ -121,6 +125,14 @@ struct PushSmem {
     u32 prevcnt[MAX_SLOTS];      // frontier size of each slot at this level (advances logbase at the next one)
     u32 i0;
     u32 step_ctr;                // dynamic hand-out of 32*PUSH_UB-edge steps inside a batch
+    // dense slot-levels (push_dense_scan)
+    unsigned char dense[MAX_SLOTS];  // this level: the slot scatters with RED and is scanned afterwards
+    unsigned char adone[MAX_SLOTS];  // this level: the slot's frontier was made by a scan, its phase A is done
+    u32 ndense;
+    u32 sc_cnt[SCAN_K * PUSH_WARPS];
+    u32 sc_wtot[PUSH_WARPS];
+    u32 sc_base;
+    u32 sc_list[SCAN_K * PUSH_THREADS]; // hit vertices of a scan tile, in vertex order
 };
 
 
@@ -141,6 +153,9 @@ __device__ __forceinline__ double atomic_add_f64_hint(double* addr, double v, u6
     double old;
     asm volatile("atom.global.add.L2::cache_hint.f64 %0, [%1], %2, %3;" : "=d"(old) : "l"(addr), "d"(v), "l"(policy) : "memory");
     return old;
+}
+__device__ __forceinline__ void red_add_f64_hint(double* addr, double v, u64 policy) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(policy) : "memory");
 }
 __device__ __forceinline__ int32_t ld_s32_hint(const int32_t* addr, u64 policy) {
     int32_t v;
@@ -182,11 +197,25 @@ __device__ __forceinline__ u64 frontier_entry(const PushArgs& a, const PushSmem<
     return __ldcs(&cur[(size_t)lo * a.n + (i - sm.fbase[lo])]);
 }
 
+template <typename OffT>
+__device__ __forceinline__ void push_flush_counters(const PushArgs& a, PushSmem<OffT>& sm) {
+    if (threadIdx.x < (u32)a.slots) {
+        const int sl = threadIdx.x;
+        const u32 v = sm.cnt_verts[sl];
+        if (v) {
+            atomicAdd(&a.edges[sl], (u64)sm.cnt_edges[sl]);
+            atomicAdd(&a.vertices[sl], (u64)v);
+            sm.cnt_edges[sl] = 0;
+            sm.cnt_verts[sl] = 0;
+        }
+    }
+}
+
 // ---- phase A: CTA `rank` of `count` takes a contiguous chunk of the frontier: snapshot + zero the
 // residues, credit the reserves, and lay the chunk's edges out on a line (eoff = exclusive scan
 // of the out-degrees; a dangling vertex owns one pseudo-edge back to its slot's source).
 // Every thread owns PUSH_UA consecutive entries and issues all their loads before using any.
-template <typename OffT>
+template <typename OffT, bool DN>
 __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& sm, const u64* cur, u32 nf, u32 level,
                                              u32 rank, u32 count) {
     const int lane = lane_id();
@@ -201,22 +230,27 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
         u32 d[PUSH_UA], lp[PUSH_UA];
 #pragma unroll
         for (int k = 0; k < PUSH_UA; ++k) e[k] = (i0 + k < hi_i) ? frontier_entry(a, sm, cur, i0 + k) : ~0ull;
+        bool ad[PUSH_UA]; // the entry's phase A was done by the scan that made it: only its edge offset is missing
 #pragma unroll
         for (int k = 0; k < PUSH_UA; ++k) {
             r[k] = rs[k] = 0.0;
             d[k] = 0;
+            ad[k] = false;
             if (e[k] != ~0ull) {
                 const int slot = entry_slot(e[k]);
                 const size_t gi = (size_t)slot * a.n + (u32)e[k];
-                // read + zero in ONE L2 operation.  (A load followed by a plain `= 0.0` store is a trap: when the compiler hoists
-                // the store right behind the load, it reaches the L2 while the sector's fill is still pending and takes a slow
-                // path -- phase A ran 3x slower.  Ordering the store behind the load by a data dependency fixed that; the
-                // exchange is 1.4 % faster still.)
-                r[k] = __longlong_as_double((long long)atomicExch((unsigned long long*)&a.residue[gi], 0ull));
-                lp[k] = sm.logbase[slot] + (i0 + k - sm.fbase[slot]);
-                if (!(a.log_v && lp[k] < a.log_cap)) {
-                    lp[k] = 0xffffffffu; // no room (or no log): direct update of the reserve
-                    rs[k] = __ldcg(&a.reserve[gi]);
+                ad[k] = DN && sm.adone[slot];
+                if (!ad[k]) {
+                    // read + zero in ONE L2 operation.  (A load followed by a plain `= 0.0` store is a trap: when the compiler hoists
+                    // the store right behind the load, it reaches the L2 while the sector's fill is still pending and takes a slow
+                    // path -- phase A ran 3x slower.  Ordering the store behind the load by a data dependency fixed that; the
+                    // exchange is 1.4 % faster still.)
+                    r[k] = __longlong_as_double((long long)atomicExch((unsigned long long*)&a.residue[gi], 0ull));
+                    lp[k] = sm.logbase[slot] + (i0 + k - sm.fbase[slot]);
+                    if (!(a.log_v && lp[k] < a.log_cap)) {
+                        lp[k] = 0xffffffffu; // no room (or no log): direct update of the reserve
+                        rs[k] = __ldcg(&a.reserve[gi]);
+                    }
                 }
                 d[k] = entry_deg24(e[k]);
                 if (d[k] == DEG_SAT) d[k] = (u32)__ldg(&a.deg[(u32)e[k]]);
@@ -231,18 +265,22 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
             if (e[k] == ~0ull) continue;
             const int slot = entry_slot(e[k]);
             const size_t gi = (size_t)slot * a.n + (u32)e[k];
-            if (lp[k] != 0xffffffffu) {
-                const size_t li = (size_t)slot * a.log_cap + lp[k];
-                a.log_v[li] = (int32_t)(u32)e[k];
-                a.log_r[li] = r[k];
-            } else {
-                a.reserve[gi] = rs[k] + r[k] * a.alpha;
+            if (!ad[k]) {
+                if (lp[k] != 0xffffffffu) {
+                    const size_t li = (size_t)slot * a.log_cap + lp[k];
+                    a.log_v[li] = (int32_t)(u32)e[k];
+                    a.log_r[li] = r[k];
+                } else {
+                    a.reserve[gi] = rs[k] + r[k] * a.alpha;
+                }
+                // increments are kept per slot segment (index inside the slot's frontier), so that a scan can write them for a
+                // frontier whose place in the next level's slot-major order is not known yet
+                a.inc[(size_t)slot * a.n + (i0 + k - sm.fbase[slot])] = d[k] ? ((1.0 - a.alpha) * r[k]) / (double)d[k] : r[k] * (1.0 - a.alpha);
+                dsum += d[k];
+                ++vcnt;
             }
-            a.inc[i0 + k] = d[k] ? ((1.0 - a.alpha) * r[k]) / (double)d[k] : r[k] * (1.0 - a.alpha);
             loc[k] = esum; // thread-local exclusive offset, completed below
             esum += d[k] ? d[k] : 1u;
-            dsum += d[k];
-            ++vcnt;
             if (slot_first < 0) slot_first = slot;
             else same = same && slot == slot_first;
         }
@@ -250,14 +288,14 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
         const int slot0 = __shfl_sync(FULL, slot_first, 0);
         if (__all_sync(FULL, same && (slot_first == slot0 || slot_first < 0))) {
             const u32 ds = warp_sum(dsum), vc = warp_sum(vcnt);
-            if (lane == 0 && slot0 >= 0) {
+            if (lane == 0 && slot0 >= 0 && vc) {
                 atomicAdd(&sm.cnt_edges[slot0], ds);
                 atomicAdd(&sm.cnt_verts[slot0], vc);
             }
         } else {
 #pragma unroll
             for (int k = 0; k < PUSH_UA; ++k)
-                if (e[k] != ~0ull) {
+                if (e[k] != ~0ull && !ad[k]) {
                     atomicAdd(&sm.cnt_edges[entry_slot(e[k])], d[k]);
                     atomicAdd(&sm.cnt_verts[entry_slot(e[k])], 1u);
                 }
@@ -272,20 +310,10 @@ __device__ __forceinline__ void push_phase_a(const PushArgs& a, PushSmem<OffT>& 
         carry += total;
     }
     if (threadIdx.x == 0) a.block_sum[rank] = carry;
-    // flush the per-slot counters of this CTA once all its warps are past their last shared atomics
+    // flush the per-slot counters of this CTA once all its warps are past their last shared atomics (a dense scan of the previous
+    // level may have left some too)
     __syncthreads();
-    if (lo_i < hi_i && threadIdx.x < (u32)a.slots) {
-        const int sl = threadIdx.x;
-        const u32 v = sm.cnt_verts[sl];
-        if (v) {
-            const int lvl = (int)(a.level_base + level + 1);
-            atomicAdd(&a.edges[sl], (u64)sm.cnt_edges[sl]);
-            atomicAdd(&a.vertices[sl], (u64)v);
-            if (a.lastlvl[sl] < lvl && atomicMax(&a.lastlvl[sl], lvl) < lvl) atomicAdd(&a.levels[sl], 1ull);
-            sm.cnt_edges[sl] = 0;
-            sm.cnt_verts[sl] = 0;
-        }
-    }
+    push_flush_counters(a, sm);
 }
 
 // append this warp's queue (entries of ONE slot) to that slot's segment of the next frontier
@@ -310,7 +338,7 @@ __device__ __forceinline__ void push_flush_warp(const PushArgs& a, const u64* my
 // flight, owners are found by binary search in shared memory, column reads are coalesced and streamed,
 // and crossing vertices collect in a private per-warp queue that is appended to the slot's next
 // frontier with one global atomic per flush.
-template <typename OffT>
+template <typename OffT, bool DN>
 __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<OffT>& g, PushSmem<OffT>& sm, const u64* cur,
                                              u32 nf, u32 level, u32 rank, u32 count, u64* nxt, u32* nxt_count) {
     const int lane = lane_id(), w = threadIdx.x >> 5;
@@ -384,7 +412,7 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
                     const bool dang = entry_deg24(e) == 0;
                     sm.G[t] = sm.base[i / cs] + __ldcg(&a.eoff[i]);
                     sm.beg[t] = beg;
-                    sm.inc[t] = __ldcg(&a.inc[i]);
+                    sm.inc[t] = __ldcg(&a.inc[(size_t)slot * a.n + (i - sm.fbase[slot])]);
                     sm.slot[t] = dang ? ~slot : slot;
                 } else {
                     sm.G[cnt] = i < nf ? sm.base[i / cs] + __ldcg(&a.eoff[i]) : E;
@@ -441,20 +469,28 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
                 // column values), so a step is two dependent memory round trips instead of three; with packed
                 // columns the degree is already there and the random load disappears for all but the largest hubs
                 int32_t du[PUSH_UB];
+                bool dn[PUSH_UB]; // dense slot-level: RED, nobody waits for the old value, the scan finds the next frontier
 #pragma unroll
                 for (int k = 0; k < PUSH_UB; ++k) {
                     du[k] = 0;
+                    dn[k] = false;
                     if (ok[k]) {
                         double* rp = &a.residue[(size_t)slot[k] * a.n + u[k]];
-                        old[k] = a.l2_hints ? atomic_add_f64_hint(rp, inc[k], pol_keep) : atomicAdd(rp, inc[k]);
-                        if (dcode[k] != dmax) du[k] = (int32_t)dcode[k];
-                        else du[k] = a.l2_hints ? ld_s32_hint(&a.deg[u[k]], pol_keep) : __ldg(&a.deg[u[k]]);
+                        dn[k] = DN && sm.dense[slot[k]];
+                        if (dn[k]) {
+                            if (a.l2_hints) red_add_f64_hint(rp, inc[k], pol_keep);
+                            else atomicAdd(rp, inc[k]);
+                        } else {
+                            old[k] = a.l2_hints ? atomic_add_f64_hint(rp, inc[k], pol_keep) : atomicAdd(rp, inc[k]);
+                            if (dcode[k] != dmax) du[k] = (int32_t)dcode[k];
+                            else du[k] = a.l2_hints ? ld_s32_hint(&a.deg[u[k]], pol_keep) : __ldg(&a.deg[u[k]]);
+                        }
                     }
                 }
 #pragma unroll
                 for (int k = 0; k < PUSH_UB; ++k) {
                     bool cross = false;
-                    if (ok[k]) {
+                    if (ok[k] && !dn[k]) {
                         const double nw = old[k] + inc[k];
                         const double thr = sm.rmax[slot[k]] * (double)du[k];
                         cross = du[k] ? (old[k] < thr && nw >= thr) : (old[k] == 0.0);
@@ -487,7 +523,111 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
     if (wq) push_flush_warp(a, myq, wq, wq_slot, nxt, nxt_count);
 }
 
+// ---- dense scan of slot s after a level in which it scattered with RED: the vertices at or above their threshold ARE the
+// frontier of level + 1 (phase A zeroed the previous frontier, so nothing else can be above), and their phase A happens here:
+// residue zeroed, credit logged, increment written.  CTA `rank` owns a contiguous range of the vector, handled in tiles of
+// SCAN_K * PUSH_THREADS vertices: pass 1 reads residue and out-degree of the tile (SCAN_K independent loads of each in flight per
+// thread) and notes the hits; a block scan of the (k, warp) counts and ONE global atomic place the tile's hits in vertex order; the
+// hit vertices are compacted into shared memory; pass 2 walks that list with all lanes busy.  The frontier comes out sorted by
+// vertex id in runs of a tile, so the next level's column reads walk the CSR forward.  Whole CTA, contains CTA barriers.
 template <typename OffT>
+__device__ __forceinline__ void push_dense_scan(const PushArgs& a, PushSmem<OffT>& sm, int s, u32 rank, u32 count, u64* nxt, u32* nxt_count) {
+    const int lane = lane_id(), w = threadIdx.x >> 5;
+    const u32 n = (u32)a.n;
+    const u32 per = (n + count - 1) / count;
+    const u32 lo = min(n, rank * per), hi = min(n, lo + per);
+    double* res = a.residue + (size_t)s * n;
+    const double rm = sm.rmax[s];
+    const u32 lb = sm.logbase[s] + sm.prevcnt[s]; // log position of the first entry of the slot's next frontier
+    u32 dsum_t = 0, vcnt_t = 0;
+    for (u32 tb = lo; tb < hi; tb += SCAN_K * PUSH_THREADS) {
+        u32 mask = 0;
+        {
+            double r[SCAN_K];
+            int32_t d[SCAN_K];
+#pragma unroll
+            for (int k = 0; k < SCAN_K; ++k) {
+                const u32 v = tb + k * PUSH_THREADS + threadIdx.x;
+                r[k] = v < hi ? __ldcg(&res[v]) : 0.0; // L2, never a stale L1 line: the REDs of other SMs just landed there
+                d[k] = v < hi ? __ldg(&a.deg[v]) : 1;  // unconditionally: one round trip instead of two
+            }
+#pragma unroll
+            for (int k = 0; k < SCAN_K; ++k) {
+                const bool hit = r[k] > 0.0 && (d[k] ? (r[k] >= rm * (double)d[k]) : true);
+                const u32 bal = __ballot_sync(FULL, hit);
+                if (hit) mask |= 1u << k;
+                if (lane == 0) sm.sc_cnt[k * PUSH_WARPS + w] = __popc(bal);
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the SCAN_K * 16 (k, warp) counts in vertex order: thread t owns count t
+        const bool own = threadIdx.x < SCAN_K * PUSH_WARPS;
+        const u32 c = own ? sm.sc_cnt[threadIdx.x] : 0u;
+        const u32 incl = warp_incl_scan(c);
+        if (lane == 31) sm.sc_wtot[w] = incl; // warps beyond the counts write 0
+        __syncthreads();
+        const u32 wt = lane < PUSH_WARPS ? sm.sc_wtot[lane] : 0u;
+        const u32 wi = warp_incl_scan(wt);
+        const u32 total = __shfl_sync(FULL, wi, PUSH_WARPS - 1);
+        const u32 before = w ? __shfl_sync(FULL, wi, w - 1) : 0u;
+        if (threadIdx.x == 0) sm.sc_base = total ? atomicAdd(&nxt_count[s], total) : 0u;
+        if (own) sm.sc_cnt[threadIdx.x] = before + incl - c; // every thread rewrites only the count it read itself
+        __syncthreads();
+        if (total) { // block-uniform
+#pragma unroll
+            for (int k = 0; k < SCAN_K; ++k) { // compact the hit vertices, in vertex order
+                const bool hit = (mask >> k) & 1u;
+                const u32 bal = __ballot_sync(FULL, hit);
+                if (hit) sm.sc_list[sm.sc_cnt[k * PUSH_WARPS + w] + __popc(bal & lanemask_lt())] = tb + k * PUSH_THREADS + threadIdx.x;
+            }
+            __syncthreads();
+            const u32 base = sm.sc_base;
+            u64* seg = nxt + (size_t)s * n;
+            double* incs = a.inc + (size_t)s * n;
+            for (u32 h0 = 0; h0 < total; h0 += 4 * PUSH_THREADS) {
+                u32 v[4], d[4];
+                double r[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const u32 h = h0 + q * PUSH_THREADS + threadIdx.x;
+                    v[q] = h < total ? sm.sc_list[h] : 0xffffffffu;
+                    r[q] = 0.0; d[q] = 0;
+                    if (v[q] != 0xffffffffu) {
+                        r[q] = __ldcg(&res[v[q]]);
+                        d[q] = (u32)__ldg(&a.deg[v[q]]);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (v[q] == 0xffffffffu) continue;
+                    const u32 j = base + h0 + q * PUSH_THREADS + threadIdx.x;
+                    res[v[q]] = 0.0;
+                    seg[j] = make_entry(s, d[q], (int32_t)v[q]);
+                    const u32 lp = lb + j;
+                    if (a.log_v && lp < a.log_cap) {
+                        const size_t li = (size_t)s * a.log_cap + lp;
+                        a.log_v[li] = (int32_t)v[q];
+                        a.log_r[li] = r[q];
+                    } else {
+                        double* rp = &a.reserve[(size_t)s * n + v[q]];
+                        *rp = __ldcg(rp) + r[q] * a.alpha;
+                    }
+                    incs[j] = d[q] ? ((1.0 - a.alpha) * r[q]) / (double)d[q] : r[q] * (1.0 - a.alpha);
+                    dsum_t += d[q];
+                    ++vcnt_t;
+                }
+            }
+        }
+        __syncthreads(); // sc_cnt / sc_base / sc_list are rewritten by the next tile
+    }
+    const u32 ds = warp_sum(dsum_t), vc = warp_sum(vcnt_t);
+    if (lane == 0 && vc) {
+        atomicAdd(&sm.cnt_edges[s], ds);
+        atomicAdd(&sm.cnt_verts[s], vc);
+    }
+}
+
+template <typename OffT, bool DN>
 __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrView<OffT> g) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char push_smem_raw[];
@@ -500,6 +640,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         sm.cnt_verts[i] = 0;
         sm.logbase[i] = (a.log_v && i < a.slots) ? a.log_cur[i] : 0u;
         sm.prevcnt[i] = 0;
+        sm.dense[i] = 0;
+        sm.adone[i] = 0;
     }
     __syncthreads();
 
@@ -514,6 +656,19 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
             if (l < a.slots) { sm.fbase[l] = i0 - c0; sm.logbase[l] += sm.prevcnt[l]; sm.prevcnt[l] = c0; }
             if (l + WARP < a.slots) { sm.fbase[l + WARP] = i1 - c1; sm.logbase[l + WARP] += sm.prevcnt[l + WARP]; sm.prevcnt[l + WARP] = c1; }
             if (l == 31) sm.fbase[a.slots] = i1;
+            // a slot that scattered with RED was scanned: its frontier is ready-made; large frontiers scatter with RED this time
+            const bool d0 = DN && c0 >= a.dense_min && c0 > 0, d1 = DN && c1 >= a.dense_min && c1 > 0;
+            if (l < a.slots) { sm.adone[l] = sm.dense[l]; sm.dense[l] = d0; }
+            if (l + WARP < a.slots) { sm.adone[l + WARP] = sm.dense[l + WARP]; sm.dense[l + WARP] = d1; }
+            const u32 nd = __popc(__ballot_sync(FULL, d0)) + __popc(__ballot_sync(FULL, d1));
+            if (l == 0) sm.ndense = nd;
+            if (blockIdx.x == 0) { // levels in which the slot pushed something
+                const int lvl = (int)(a.level_base + level + 1);
+                if (level < a.max_levels) {
+                    if (l < a.slots && c0 && a.lastlvl[l] < lvl) { a.lastlvl[l] = lvl; atomicAdd(&a.levels[l], 1ull); }
+                    if (l + WARP < a.slots && c1 && a.lastlvl[l + WARP] < lvl) { a.lastlvl[l + WARP] = lvl; atomicAdd(&a.levels[l + WARP], 1ull); }
+                }
+            }
         }
         __syncthreads();
         const u32 nf = sm.fbase[a.slots];
@@ -539,16 +694,23 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
                 }
             }
         }
-        push_phase_a<OffT>(a, sm, cur, nf, level, blockIdx.x, gridDim.x);
+        push_phase_a<OffT, DN>(a, sm, cur, nf, level, blockIdx.x, gridDim.x);
         grid.sync();
         if (blockIdx.x == 0 && threadIdx.x == 0 && a.trace && level < a.trace_cap) {
             u64 t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
             a.trace[4 * level + 3] = t;
         }
-        push_phase_b<OffT>(a, g, sm, cur, nf, level, blockIdx.x, gridDim.x, nxt, nxt_count);
+        push_phase_b<OffT, DN>(a, g, sm, cur, nf, level, blockIdx.x, gridDim.x, nxt, nxt_count);
         grid.sync();
+        if (DN && sm.ndense) { // the slots that scattered with RED: next frontier + its phase A from one pass over the residue vector
+            for (int s = 0; s < a.slots; ++s)
+                if (sm.dense[s]) push_dense_scan<OffT>(a, sm, s, blockIdx.x, gridDim.x, nxt, nxt_count);
+            grid.sync();
+        }
     }
+    __syncthreads();
+    push_flush_counters(a, sm); // what the last scans counted
     // every CTA holds the same log positions; CTA 0 publishes them for the next launch of the wave / the apply pass
     if (a.log_v && blockIdx.x == 0 && threadIdx.x < (u32)a.slots) a.log_cur[threadIdx.x] = sm.logbase[threadIdx.x] + sm.prevcnt[threadIdx.x];
 }

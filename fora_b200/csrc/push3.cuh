@@ -131,10 +131,6 @@ __device__ __forceinline__ int p3_slot_of(const P3Smem& sm, int s0, int s1, u32 
     return lo;
 }
 
-__device__ __forceinline__ void red_add_f64_hint(double* addr, double v, u64 policy) {
-    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(policy) : "memory");
-}
-
 // streamed once per level: keep them out of the way of the residue vector the grid is working on
 __device__ __forceinline__ u64 ld_u64_stream(const u64* addr, u64 policy) {
     u64 v;

@@ -198,6 +198,8 @@ print("RESULT" + json.dumps(out))
                 {"FORA_PUSH_V": "2", "FORA_PUSH_SUB": "1", "FORA_TAIL_NF": "2048", "FORA_TAIL_E": "100000"},
                 {"FORA_PUSH_V": "2", "FORA_PUSH_SUB": "8", "FORA_TAIL_NF": "0", "FORA_PUSH_PREFETCH": "0"},
                 # lockstep kernel (push3.cuh): one group per level, one slot per group, hubs cut into small pieces, plain atomics
+                # first-generation kernel with dense slot-levels (RED + scan of the residue vector): always / from 1 % of the vertices
+                {"FORA_PUSH_V": "1", "FORA_PUSH_DENSE": "0"}, {"FORA_PUSH_V": "1", "FORA_PUSH_DENSE": "0.01", "FORA_PUSH_LOG": "0"},
                 # (push3.cuh) default thresholds; every slot-level dense (RED + scan); never dense with tiny groups; hubs cut into
                 # small pieces in both modes; plain atomics and no credit log
                 {"FORA_PUSH_V": "3"}, {"FORA_PUSH_V": "3", "FORA_P3_DENSE": "0"}, {"FORA_PUSH_V": "3", "FORA_P3_DENSE": "-1", "FORA_P3_BUDGET": "0.002"},
