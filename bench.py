@@ -345,6 +345,25 @@ def main():
     barrier()
     e2e_dense = world * nqd / (shard.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
     checksum = float(ppr_np.sum(axis=1).mean())  # each PPR vector sums to 1
+    del h_ppr, ppr_np
+
+    # ---- opt-in mode, reported next to the headline (never instead of it): the queries of a wave draw their walks from one
+    # pool (fora_ctx_set_shared_walks, include/fora_b200.h) -- same timed region as `value`, two steps
+    E.set_shared_walks(True)
+    E.set_query_base(rank * B)
+    E.query_batch_device("fora", d_src[0].data_ptr(), B)
+    barrier()
+    e0.record(stream)
+    sw_steps, sw_walk_ms, sw_push_ms = 2, 0.0, 0.0
+    for i in range(sw_steps):
+        E.set_query_base(((args.warmup + i) * world + rank) * B)
+        _, tm = E.query_batch_device("fora", d_src[args.warmup + i].data_ptr(), B)
+        sw_walk_ms += tm["walk_ms"]
+        sw_push_ms += tm["push_ms"]
+    e1.record(stream)
+    barrier()
+    sw_value = world * B * sw_steps / (shard.max_over_ranks(e0.elapsed_time(e1)) / 1e3)
+    E.set_shared_walks(False)
 
     if rank == 0:
         peaks, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
@@ -394,6 +413,11 @@ def main():
                             "(what FORA's guarantee covers; %.4f of the PPR mass per query) plus the offsets" % sp_mass},
             "e2e_dense": {"value": e2e_dense, "unit": "queries/s", "h2d_bytes_per_step": int(4 * nqd), "d2h_bytes_per_step": int(8 * n * nqd), "queries_per_step": nqd,
                           "note": "fora_query_batch: the full dense fp64 PPR vector per query out to pinned host memory (worst case); mean vector sum %.9f" % checksum},
+            "opt_in_shared_walks": {"value": sw_value, "unit": "queries/s", "steps": sw_steps, "walk_phase_ms_per_query": sw_walk_ms / (B * sw_steps),
+                                    "push_phase_ms_per_query": sw_push_ms / (B * sw_steps),
+                                    "note": "NOT the headline: fora_ctx_set_shared_walks(1) -- the %d queries of a wave draw their walks from one pool built per wave "
+                                            "(the reference's --with_idx sharing, query.h:290-307, without a stored index); per-query guarantee unchanged, estimates "
+                                            "of queries of the same wave correlated" % args.slots},
             "gpu_launches": int(agg["kernel_launches"]),
             "roofline": roofline,
             "cpu_baseline": cpu,

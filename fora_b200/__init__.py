@@ -110,6 +110,7 @@ def lib():
     L.fora_ctx_set_slots.argtypes = [vp, C.c_int]
     L.fora_ctx_sync.argtypes = [vp]
     L.fora_ctx_set_query_base.argtypes = [vp, C.c_uint64]
+    L.fora_ctx_set_shared_walks.argtypes = [vp, C.c_int]
     L.fora_graph_upload.argtypes = [vp, C.c_int32, C.c_int64, c_lp, c_ip, c_lp, c_ip]
     L.fora_graph_build_from_edges.argtypes = [vp, C.c_int32, C.c_int64, c_ip, c_ip, C.c_int64, C.c_int]
     L.fora_graph_download_csr.argtypes = [vp, c_lp, c_ip, c_lp, c_ip]
@@ -255,6 +256,10 @@ class Engine:
     def set_query_base(self, first_query_index):
         """global list index of the first query of the next batch call (Philox key), see include/fora_b200.h"""
         self._ck(self.L.fora_ctx_set_query_base(self.h, int(first_query_index)))
+
+    def set_shared_walks(self, on=True):
+        """opt-in: the queries of one wave draw their walks from one pool (per-wave virtual walk index), see include/fora_b200.h"""
+        self._ck(self.L.fora_ctx_set_shared_walks(self.h, 1 if on else 0))
 
     # --- graph
     def upload_graph(self, n, m_decl, out_ptr, out_col, in_ptr=None, in_col=None):

@@ -195,6 +195,17 @@ struct fora_ctx {
     u32 level_base = 0;
     u64 launches = 0;
     u64 qid_base = 0; // global index of the first query of the next batch call (Philox key); see fora_ctx_set_query_base
+    // shared walks (fora_ctx_set_shared_walks): a per-wave virtual walk index
+    int shared_walks = 0;
+    DevBuf<u32> sw_cnt;        // [n] walks needed from each vertex = max over the wave's slots
+    DevBuf<u64> sw_cnt64, sw_off; // [n] the same as the index arrays the walk kernel reads
+    DevBuf<u32> sw_flag, sw_pos;  // [n] vertices with walks, their rank
+    DevBuf<int32_t> sw_srcs;   // [n] those vertices, compacted
+    DevBuf<u64> sw_woff;       // [n + 1] exclusive prefix of their counts
+    DevBuf<int32_t> sw_dest;   // destinations, internal ids
+    DevBuf<unsigned char> sw_tmp; // cub scratch
+    u64 sw_waves = 0;          // waves served so far (Philox key of a wave's walks)
+    u64 sw_built_walks = 0, sw_built_hops = 0; // of the last wave
     // resumable push session (fora_push_begin / fora_push_round)
     int32_t session_source = -1;
 
@@ -339,6 +350,11 @@ extern "C" int fora_ctx_set_slots(fora_ctx* ctx, int slots) {
 extern "C" int fora_ctx_set_query_base(fora_ctx* ctx, uint64_t first_query_index) {
     if (!ctx) return FORA_EINVAL;
     ctx->qid_base = first_query_index;
+    return FORA_OK;
+}
+extern "C" int fora_ctx_set_shared_walks(fora_ctx* ctx, int on) {
+    if (!ctx) return FORA_EINVAL;
+    ctx->shared_walks = on ? 1 : 0;
     return FORA_OK;
 }
 extern "C" int fora_ctx_sync(fora_ctx* ctx) {
@@ -1362,6 +1378,51 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
 // holding the reserve on entry).  round_tag distinguishes the Philox streams of top-k rounds.
 // groups > 1 launches the walk kernel once per group of slots and calls after_group(lo, hi) behind each launch, so a
 // caller can ship finished slots while the remaining ones still walk.
+// ---------------------------------------------------------------------------------------------
+// Shared walks (opt-in, fora_ctx_set_shared_walks): the wave's queries draw their walks from ONE pool.  Walk j from vertex v is
+// computed once per wave and serves every query of the wave that needs at least j + 1 walks from v -- the reference's own
+// --with_idx semantics (query.h:290-307: every query reads the same stored destinations), with the index sized by what the wave
+// needs (max over its slots of n_v), rebuilt with fresh randomness for every wave and never stored.  Each query's estimate keeps
+// its distribution (its walks are independent samples of the walk from v); estimates of queries of the SAME wave are correlated.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sw_max_kernel(int32_t n, const int32_t* __restrict__ srcs, const u64* __restrict__ woff,
+                                                     const u64* __restrict__ nsrc, const int32_t* __restrict__ slot_state, u32* __restrict__ cnt) {
+    const int slot = blockIdx.y;
+    if (slot_state[slot] != 1) return;
+    const u64 ns = nsrc[slot];
+    const int32_t* __restrict__ sv = srcs + (size_t)slot * n;
+    const u64* __restrict__ wo = woff + (size_t)slot * (n + 1);
+    for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < ns; i += (u64)gridDim.x * blockDim.x) {
+        const u64 c = wo[i + 1] - wo[i];
+        atomicMax(&cnt[sv[i]], (u32)min(c, (u64)0xffffffffu));
+    }
+}
+__global__ void __launch_bounds__(256) sw_flag_kernel(int32_t n, const u32* __restrict__ cnt, u64* __restrict__ cnt64, u32* __restrict__ flag) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        cnt64[v] = cnt[v];
+        flag[v] = cnt[v] != 0;
+    }
+}
+__global__ void __launch_bounds__(256) sw_compact_kernel(int32_t n, const u32* __restrict__ cnt, const u32* __restrict__ pos,
+                                                         const u64* __restrict__ off, int32_t* __restrict__ srcs, u64* __restrict__ woff,
+                                                         u64* __restrict__ totals /* [2]: sources, walks */) {
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+        if (cnt[v]) {
+            srcs[pos[v]] = v;
+            woff[pos[v]] = off[v];
+        }
+        if (v == n - 1) {
+            const u64 ns = pos[v] + (cnt[v] != 0), nw = off[v] + cnt[v];
+            woff[ns] = nw;
+            totals[0] = ns;
+            totals[1] = nw;
+        }
+    }
+}
+struct BulkPlan;
+static int launch_bulk(fora_ctx* ctx, const BulkPlan& bp, u64* hops_out, int parts, const std::function<int(int, u64, u64)>& after_part);
+static int build_shared_walks(fora_ctx* ctx, int no_zero_hop);
+
 static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_zero_hop, u32 round_tag, const u64* idx_used,
                      u32 part = 0, u32 nparts = 1, int groups = 1, const std::function<int(int, int)>& after_group = nullptr) {
     const DeviceGraph& g = ctx->g;
@@ -1388,11 +1449,20 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.alpha_thr = (u32)std::min(4294967295.0, ctx->p.alpha * 4294967296.0);
     wa.seed_lo = (u32)ctx->seed; wa.seed_hi = (u32)(ctx->seed >> 32);
     wa.with_idx = ctx->p.with_idx && ctx->has_index;
+    const bool shared = ctx->shared_walks && !wa.with_idx && per_round == 0 && nparts == 1 && !idx_used;
+    if (shared) {
+        int brc = build_shared_walks(ctx, no_zero_hop);
+        if (brc) return brc;
+    }
     wa.srcs = ctx->srcs.p; wa.woff = ctx->woff.p; wa.incs = ctx->incs.p; wa.nsrc = m->nsrc; wa.nwalk = m->nwalk;
     wa.chunk_first = ctx->chunk_first.p; wa.chunk_cap = ctx->chunk_cap; wa.slot_state = m->state; wa.qid = m->qid;
     wa.part = part; wa.nparts = nparts;
     wa.round_tag = round_tag; wa.ppr = ppr; wa.hops = m->hops; wa.idx_hits = m->idx_hits;
     wa.idx_off = ctx->idx_off.p; wa.idx_cnt = ctx->idx_cnt.p; wa.idx_dest = ctx->idx_dest.p; wa.idx_used = idx_used;
+    if (shared) { // every walk of the wave is a hit in the pool just built
+        wa.with_idx = 1;
+        wa.idx_off = ctx->sw_off.p; wa.idx_cnt = ctx->sw_cnt64.p; wa.idx_dest = ctx->sw_dest.p; wa.idx_used = nullptr;
+    }
     // neighbour slots beyond the first 32 MB of the (hot-first) column array stream through the L2 with evict_first
     // (measured: 16..64 MB within 1 %, +2.6 % hops/s over no hint)
     wa.hot_elems = (u64)((getenv("FORA_WALK_HOT_MB") ? atof(getenv("FORA_WALK_HOT_MB")) : 32.0) * 262144.0);
@@ -1589,6 +1659,7 @@ struct BulkPlan {
     u64* out_counts = nullptr;       // ... or device [n] histogram in internal ids (OUT_COUNT)
     u32 key_tag = 0;                 // distinguishes index build / MC / BiPPR / test streams
     int no_zero_hop = 0;
+    int internal_ids = 0;            // OUT_DEST: keep the engine's internal vertex ids (a per-wave virtual index)
 };
 struct BulkMeta { // what walk_kernel reads per slot; slot 0 of a private block
     u64 nsrc, nwalk, hops, idx_hits;
@@ -1597,7 +1668,8 @@ struct BulkMeta { // what walk_kernel reads per slot; slot 0 of a private block
 };
 // parts > 1: one launch per contiguous chunk range, after_part(part, first walk, end walk) behind each (e.g. to ship that slice)
 static int launch_bulk(fora_ctx* ctx, const BulkPlan& bp, u64* hops_out, int parts = 1,
-                       const std::function<int(int, u64, u64)>& after_part = nullptr) {
+                       const std::function<int(int, u64, u64)>& after_part = nullptr);
+static int launch_bulk(fora_ctx* ctx, const BulkPlan& bp, u64* hops_out, int parts, const std::function<int(int, u64, u64)>& after_part) {
     const DeviceGraph& g = ctx->g;
     if (hops_out) *hops_out = 0;
     if (bp.nwalk == 0) return FORA_OK;
@@ -1620,7 +1692,7 @@ static int launch_bulk(fora_ctx* ctx, const BulkPlan& bp, u64* hops_out, int par
     wa.srcs = bp.d_srcs; wa.woff = bp.d_woff; wa.incs = nullptr; wa.nsrc = &dm->nsrc; wa.nwalk = &dm->nwalk;
     wa.chunk_first = ctx->bulk_chunk_first.p; wa.chunk_cap = (size_t)(nchunks + 2); wa.slot_state = &dm->state; wa.qid = &dm->qid;
     wa.round_tag = 0x5bd1e995u; wa.hops = &dm->hops; wa.idx_hits = &dm->idx_hits;
-    wa.out_dest = bp.out_dest; wa.out_counts = bp.out_counts; wa.new2old = g.relabeled ? g.new2old : nullptr;
+    wa.out_dest = bp.out_dest; wa.out_counts = bp.out_counts; wa.new2old = (g.relabeled && !bp.internal_ids) ? g.new2old : nullptr;
     parts = (int)std::max<u64>(1, std::min<u64>((u64)parts, nchunks));
     wa.nparts = (u32)parts;
     const bool to_dest = bp.out_dest != nullptr;
@@ -1674,6 +1746,47 @@ static int launch_bulk_single(fora_ctx* ctx, int32_t source_internal, u64 count,
     bp.d_woff = ctx->bulk_small.p;
     bp.nsrc = 1; bp.nwalk = count; bp.out_dest = out_dest; bp.out_counts = out_counts; bp.key_tag = key_tag; bp.no_zero_hop = no_zero_hop;
     return launch_bulk(ctx, bp, hops_out);
+}
+
+// the wave's walk pool: counts (max over slots), offsets, compacted plan, destinations (see sw_max_kernel)
+static int build_shared_walks(fora_ctx* ctx, int no_zero_hop) {
+    const DeviceGraph& g = ctx->g;
+    const size_t n = (size_t)g.n;
+    const int S = ctx->slots;
+    SlotMeta* m = ctx->meta.p;
+    CK(ctx->sw_cnt.ensure(n)); CK(ctx->sw_cnt64.ensure(n)); CK(ctx->sw_off.ensure(n)); CK(ctx->sw_flag.ensure(n)); CK(ctx->sw_pos.ensure(n));
+    CK(ctx->sw_srcs.ensure(n)); CK(ctx->sw_woff.ensure(n + 3));
+    CK(cudaMemsetAsync(ctx->sw_cnt.p, 0, sizeof(u32) * n, ctx->stream));
+    sw_max_kernel<<<dim3(ctx->num_sms * 4, S), 256, 0, ctx->stream>>>(g.n, ctx->srcs.p, ctx->woff.p, m->nsrc, m->state, ctx->sw_cnt.p);
+    CKL();
+    sw_flag_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(g.n, ctx->sw_cnt.p, ctx->sw_cnt64.p, ctx->sw_flag.p);
+    CKL();
+    size_t t1 = 0, t2 = 0;
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t1, ctx->sw_cnt64.p, ctx->sw_off.p, (int)n, ctx->stream));
+    CK(cub::DeviceScan::ExclusiveSum(nullptr, t2, ctx->sw_flag.p, ctx->sw_pos.p, (int)n, ctx->stream));
+    size_t tb = std::max(t1, t2);
+    CK(ctx->sw_tmp.ensure(tb));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->sw_tmp.p, tb, ctx->sw_cnt64.p, ctx->sw_off.p, (int)n, ctx->stream));
+    CK(cub::DeviceScan::ExclusiveSum(ctx->sw_tmp.p, tb, ctx->sw_flag.p, ctx->sw_pos.p, (int)n, ctx->stream));
+    u64* d_tot = ctx->sw_woff.p + n + 1; // two spare words behind the prefix
+    sw_compact_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(g.n, ctx->sw_cnt.p, ctx->sw_pos.p, ctx->sw_off.p, ctx->sw_srcs.p, ctx->sw_woff.p, d_tot);
+    CKL();
+    u64 tot[2] = {0, 0};
+    CK(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->sw_built_walks = tot[1];
+    ctx->sw_built_hops = 0;
+    if (tot[1] == 0) return FORA_OK;
+    CK(ctx->sw_dest.ensure((size_t)tot[1]));
+    BulkPlan bp;
+    bp.d_srcs = ctx->sw_srcs.p; bp.d_woff = ctx->sw_woff.p; bp.nsrc = tot[0]; bp.nwalk = tot[1]; bp.out_dest = ctx->sw_dest.p;
+    // one stream per wave: ctx seed x global index of the wave's first query (reproducible; a different cut of the query list into
+    // waves gives different pools)
+    bp.key_tag = 0x5a000000u ^ ctx->h_meta->qid[0];
+    bp.no_zero_hop = no_zero_hop;
+    bp.internal_ids = 1;
+    ++ctx->sw_waves;
+    return launch_bulk(ctx, bp, nullptr, 1, nullptr);
 }
 
 extern "C" int fora_random_walks(fora_ctx* ctx, int32_t start, int64_t count, int no_zero_hop, int32_t* dest, uint64_t* hops) {

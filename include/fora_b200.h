@@ -71,6 +71,13 @@ int fora_ctx_sync(fora_ctx* ctx);
  * index of the first query of the next fora_query_batch* / fora_topk_batch call here so that no two queries of a run share a
  * random stream and results do not depend on how the list was cut.  Sticky; 0 after fora_ctx_create. */
 int fora_ctx_set_query_base(fora_ctx* ctx, uint64_t first_query_index);
+/* Opt-in: the queries of one wave (fora_ctx_set_slots of them at a time) draw their random walks from ONE pool.  Walk j from
+ * vertex v is computed once per wave and serves every query of the wave that needs more than j walks from v -- what the
+ * reference does for ALL queries when it runs --with_idx (query.h:290-307), here with a pool sized by the wave's own needs,
+ * rebuilt with fresh randomness for every wave and never stored.  Every query's estimate keeps its distribution and FORA's
+ * guarantee; the estimates of queries of the same wave are no longer independent of each other.  Applies to the plain query
+ * path (fora_query_batch* with algo fora, no index, one GPU per query); 0 (default) = every query walks for itself. */
+int fora_ctx_set_shared_walks(fora_ctx* ctx, int on);
 
 /* ------------------------------------------------------------------------------------------
  * Graph  (Graph graph(folder), fora.cpp:176-177 -> graph.h:37-46,89-163)

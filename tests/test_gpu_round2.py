@@ -157,6 +157,37 @@ def test_index_build_stats_and_bulk_walk_distribution(g):
     E.close()
 
 
+def test_shared_walks_keep_the_guarantee_and_walk_once(g):
+    # opt-in per-wave walk pool (fora_ctx_set_shared_walks): every walk of every query is a hit in the pool, each query still meets
+    # FORA's (eps, 1/n) guarantee against exact PPR, the push state is untouched, and the pool is smaller than the sum of the walks
+    E = fb.Engine(0, seed=5, slots=8)
+    E.upload_graph(g.n, g.m_decl, g.out_ptr, g.out_col)
+    E.configure("fora", 0.5, opt=1, balanced=1)
+    srcs = np.array([3, 77, int(np.argmax(g.deg)), 1500, 9, 4000, 123, 2500, 31, 600], np.int32)  # two waves, the second ragged
+    base, st0, _ = E.query_batch("fora", srcs)
+    E.set_shared_walks(True)
+    ppr, st1, _ = E.query_batch("fora", srcs)
+    again, _, _ = E.query_batch("fora", srcs)
+    assert np.abs(ppr - again).max() < 1e-12  # the pool is keyed by the wave's first global query index: reproducible
+    bad = total = 0
+    for i, s in enumerate(srcs):
+        assert st1[i]["n_walks"] == st0[i]["n_walks"] and st1[i]["edges_pushed"] == st0[i]["edges_pushed"]
+        assert st1[i]["n_idx_hits"] == st1[i]["n_walks"] and st1[i]["walk_hops"] == 0
+        assert abs(ppr[i].sum() - 1.0) < 1e-9
+        exact = E.power_iteration(int(s), 150)
+        big = exact >= 1.0 / g.n
+        rel = np.abs(ppr[i][big] - exact[big]) / exact[big]
+        bad += int((rel > 0.5).sum())
+        total += int(big.sum())
+        if st1[i]["n_walks"] > 1000:
+            assert np.abs(ppr[i] - base[i]).max() > 0  # other walks than the private ones
+    assert bad <= max(1, total // g.n), (bad, total)
+    E.set_shared_walks(False)
+    back, _, _ = E.query_batch("fora", srcs)
+    assert np.abs(back - base).max() < 1e-12
+    E.close()
+
+
 def test_push_generations_agree():
     # the sub-wave / tail kernels (push2.cuh) and the first-generation kernel produce the same push: identical work
     # counters, values equal up to the order of fp64 additions; several sub-wave sizes and tail thresholds
