@@ -1095,6 +1095,11 @@ static PushArgs make_push_args(fora_ctx* ctx) {
         const double f = getenv("FORA_PUSH_DENSE") ? atof(getenv("FORA_PUSH_DENSE")) : -1.0;
         a.dense_min = f < 0 ? 0xffffffffu : (u32)std::max(1.0, f * (double)ctx->g.n);
     }
+    // lockstep phase B (FORA_PUSH_LOCKSTEP = group size in units of n edges, e.g. 0.125; unset / 0: off)
+    {
+        const double f = getenv("FORA_PUSH_LOCKSTEP") ? atof(getenv("FORA_PUSH_LOCKSTEP")) : 0.0;
+        a.lockstep_edges = f > 0 ? (u64)std::max(1.0, f * (double)ctx->g.n) : 0;
+    }
     return a;
 }
 
@@ -1476,6 +1481,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
         int wrc = set_l2_window(ctx, ctx->win_walk_off, ctx->win_walk_bytes);
         if (wrc) return wrc;
     }
+    if (getenv("FORA_WALK_GROUPS")) groups = std::max(groups, atoi(getenv("FORA_WALK_GROUPS"))); // development knob: slots per launch = S / groups
     groups = std::max(1, std::min(groups, S));
     for (int gi = 0; gi < groups; ++gi) {
         const int lo = (int)((long long)S * gi / groups), hi = (int)((long long)S * (gi + 1) / groups);

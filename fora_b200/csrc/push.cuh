@@ -105,6 +105,9 @@ struct PushArgs {
     // dense slot-levels: a slot whose frontier has at least dense_min entries scatters with RED (no return value) and its next
     // frontier is found by one scan of its residue vector, which also does that frontier's phase A (0xffffffff: never)
     u32 dense_min;
+    // lockstep phase B: the edge line is worked through in groups of whole slots of at least this many edges, with a grid barrier
+    // between groups, so that the grid never has more than one or two residue vectors live in the L2 (0: one sweep, no barriers)
+    u64 lockstep_edges;
 };
 
 // dynamic shared memory of the push kernel (~70 KB, two CTAs per SM)
@@ -133,6 +136,7 @@ struct PushSmem {
     u32 sc_wtot[PUSH_WARPS];
     u32 sc_base;
     u32 sc_list[SCAN_K * PUSH_THREADS]; // hit vertices of a scan tile, in vertex order
+    u64 gslot[MAX_SLOTS + 1];           // lockstep phase B: where each slot starts on the level's edge line
 };
 
 
@@ -360,8 +364,13 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
     const u64 E = sm.base[count];
     if (a.trace && rank == 0 && threadIdx.x == 0 && level < a.trace_cap) a.trace[4 * level + 2] = E;
     if (E == 0) return;
-    u64 T = (E + count - 1) / count;
-    T = T < TILE_MIN ? TILE_MIN : (T > a.tile_max ? a.tile_max : T);
+    if (a.lockstep_edges) {
+        for (u32 t = threadIdx.x; t <= (u32)a.slots; t += PUSH_THREADS) {
+            const u32 i = sm.fbase[t];
+            sm.gslot[t] = i < nf ? sm.base[i / cs] + __ldcg(&a.eoff[i]) : E;
+        }
+        __syncthreads();
+    }
     const u64 pol_keep = l2_policy_evict_last(), pol_stream = l2_policy_evict_first();
     u32 wq = 0;       // entries in this warp's queue (warp-uniform register)
     int wq_slot = 0;  // the slot they belong to
@@ -369,8 +378,18 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
     // (Rejected after measurement: tiles claimed dynamically from a cursor with guided, shrinking sizes -- 16.7 instead
     // of 18.4 G edges/s; a tile start costs a 32-ary search in global memory plus a full batch staging, so fewer,
     // larger static tiles win although the grid barrier then waits for the CTAs that drew one tile more.)
-    for (u64 lo = (u64)rank * T; lo < E; lo += (u64)count * T) {
-        const u64 hi = min(E, lo + T);
+    int gs = 0;
+    for (u64 g_lo = 0; g_lo < E;) {
+    u64 g_hi = E;
+    if (a.lockstep_edges) { // the group ends at the first slot boundary that leaves it at least lockstep_edges edges
+        while (gs < a.slots && sm.gslot[gs] <= g_lo) ++gs; // first slot that starts behind g_lo
+        while (gs < a.slots && sm.gslot[gs] - g_lo < a.lockstep_edges) ++gs;
+        if (gs < a.slots) g_hi = sm.gslot[gs];
+    }
+    u64 T = (g_hi - g_lo + count - 1) / count;
+    T = T < TILE_MIN ? TILE_MIN : (T > a.tile_max ? a.tile_max : T);
+    for (u64 lo = g_lo + (u64)rank * T; lo < g_hi; lo += (u64)count * T) {
+        const u64 hi = min(g_hi, lo + T);
         // first entry of the tile: largest i with G(i) <= lo, G(i) = base[i / cs] + eoff[i]
         if (w == 0) {
             u32 c = 0; // largest chunk with base[c] <= lo (only trailing chunks are empty, and they sit at E)
@@ -519,6 +538,9 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
             if (!more) break;
             i_cur += cnt;
         }
+    }
+    g_lo = g_hi;
+    if (g_lo < E) cg::this_grid().sync(); // every CTA sees the same groups
     }
     if (wq) push_flush_warp(a, myq, wq, wq_slot, nxt, nxt_count);
 }
