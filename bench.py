@@ -356,8 +356,9 @@ def main():
     e0.record(stream)
     sw_steps, sw_walk_ms, sw_push_ms = 2, 0.0, 0.0
     for i in range(sw_steps):
-        E.set_query_base(((args.warmup + i) * world + rank) * B)
-        _, tm = E.query_batch_device("fora", d_src[args.warmup + i].data_ptr(), B)
+        j = (args.warmup + i) % steps_total  # (any --steps / --warmup combination)
+        E.set_query_base((j * world + rank) * B)
+        _, tm = E.query_batch_device("fora", d_src[j].data_ptr(), B)
         sw_walk_ms += tm["walk_ms"]
         sw_push_ms += tm["push_ms"]
     e1.record(stream)

