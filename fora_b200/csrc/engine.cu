@@ -1471,6 +1471,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.idx_off = ctx->idx_off.p; wa.idx_cnt = ctx->idx_cnt.p; wa.idx_dest = ctx->idx_dest.p; wa.idx_used = idx_used;
     if (shared) { // every walk of the wave is a hit in the pool just built
         wa.with_idx = 1;
+        wa.all_idx = 1;
         wa.idx_off = ctx->sw_off.p; wa.idx_cnt = ctx->sw_cnt64.p; wa.idx_dest = ctx->sw_dest.p; wa.idx_used = nullptr;
     }
     // neighbour slots beyond the first 32 MB of the (hot-first) column array stream through the L2 with evict_first
@@ -1494,7 +1495,15 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
         wa.slot0 = lo;
         const dim3 grid(wgx, hi - lo);
         kev_begin(ctx, 1);
-        if (g.off32) {
+        if (wa.all_idx) { // shared walks: lookups in the wave's pool, nothing is walked
+            if (g.off32) {
+                CsrView<u32> v{ctx->hot_ptr32, g.out_col};
+                walk_kernel<u32, false, false, OUT_POOL><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            } else {
+                CsrView<int64_t> v{g.out_ptr64, g.out_col};
+                walk_kernel<int64_t, false, false, OUT_POOL><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);
+            }
+        } else if (g.off32) {
             CsrView<u32> v{ctx->hot_ptr32, g.out_col};
             if (wa.hot_elems && wa.hot_elems < (u64)g.n_edges) {
                 if (no_zero_hop) walk_kernel<u32, true, true><<<grid, WALK_THREADS, 0, ctx->stream>>>(wa, v);

@@ -254,6 +254,7 @@ struct WalkArgs {
     const u64* __restrict__ idx_cnt;
     const int32_t* __restrict__ idx_dest;
     const u64* __restrict__ idx_used; // per-round cursor (top-k), may be null
+    int all_idx;                      // shared walks (OUT_POOL instantiation): every walk is a hit in the pool, no walk is taken
     u32 part, nparts;                 // multi-GPU walk split: this launch walks chunks [part*C/nparts, (part+1)*C/nparts)
     int slot0;                        // first slot of this launch (blockIdx.y counts from it)
     u64 hot_elems;                    // HINT instantiation: neighbour slots from this position on are loaded with L2 evict_first
@@ -263,7 +264,7 @@ struct WalkArgs {
     u64* out_counts;                  // OUT_COUNT: out_counts[destination] += 1 (internal ids)
     const int32_t* __restrict__ new2old;
 };
-enum { OUT_PPR = 0, OUT_DEST = 1, OUT_COUNT = 2 };
+enum { OUT_PPR = 0, OUT_DEST = 1, OUT_COUNT = 2, OUT_POOL = 3 }; // OUT_POOL: shared walks, every walk of the launch is read from the wave's pool
 
 // The walk itself.  Semantics of algo.h:124-166: a start with no out-edges returns itself; each
 // step first stops with probability alpha (skipped once when NO_ZERO_HOP), then moves to a uniform
@@ -344,6 +345,32 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, CsrView<
             s_own[x] = (unsigned short)lo;
         }
         __syncthreads();
+
+        if (OUT == OUT_POOL) {
+            // shared walks: EVERY walk of the chunk is a hit in the wave's pool (idx_cnt[v] >= n_v by construction), so there is nothing
+            // to walk and nothing to balance: walk x is read and added by thread x mod 256, four independent lookups in flight
+            for (u32 x0 = threadIdx.x; x0 < nw; x0 += 4 * WALK_THREADS) {
+                int32_t dest[4];
+                double winc[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const u32 x = x0 + q * WALK_THREADS;
+                    dest[q] = -1;
+                    if (x < nw) {
+                        const u32 own = s_own[x];
+                        const u64 j = own ? (u64)(x - (u32)s_rel[own]) : (u64)((long long)x - s_rel0);
+                        const int32_t v = srcs[s_lo + own];
+                        winc[q] = incs[s_lo + own];
+                        dest[q] = __ldcs(&a.idx_dest[a.idx_off[v] + j]);
+                        ++my_hits;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (dest[q] >= 0) atomicAdd(&ppr[dest[q]], winc[q]);
+            }
+            continue;
+        }
 
         int32_t cur = 0, start = 0;
         u32 jlo = 0, jhi = 0, blk = 0, myx = 0;
