@@ -174,6 +174,10 @@ struct fora_ctx {
     double p3_budget = 1.0; // a group's estimated scatter footprint, in residue vectors
     u32 p3_hub_deg = P3_HUB_DEG, p3_hub_piece = P3_HUB_PIECE;
     double p3_dense = 1.0 / 32;
+    // first-generation kernel, dense slot-levels: edge lists (push.cuh push_dense_scan / push_el_adds)
+    DevBuf<uint2> el;
+    DevBuf<u32> el_ctl; // [2][MAX_SLOTS] counts, [2][MAX_SLOTS] overflow flags
+    size_t el_cap = 0;
     // bulk walks (index build / Monte-Carlo / BiPPR) through the chunked walk kernel
     DevBuf<u32> bulk_chunk_first;
     DevBuf<unsigned char> bulk_meta;
@@ -885,6 +889,14 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
             CK(ctx->log_v.ensure(ctx->log_cap * S));
             CK(ctx->log_r.ensure(ctx->log_cap * S));
         }
+        ctx->el_cap = 0;
+        if (getenv("FORA_PUSH_DENSE") && atof(getenv("FORA_PUSH_DENSE")) >= 0 && g.off32 && !(getenv("FORA_PUSH_EL") && atoi(getenv("FORA_PUSH_EL")) == 0)) {
+            // a slot-level's edges: at most the graph's; 2n covers every level of the graphs measured (LJ shape peaks at 0.85 n)
+            ctx->el_cap = (size_t)std::min<int64_t>(g.n_edges, 2 * (int64_t)n);
+            CK(ctx->el.ensure(2 * (size_t)S * ctx->el_cap));
+            CK(ctx->el_ctl.ensure(4 * MAX_SLOTS));
+            CK(cudaMemsetAsync(ctx->el_ctl.p, 0, sizeof(u32) * 4 * MAX_SLOTS, ctx->stream));
+        }
         ctx->trace_on = getenv("FORA_PUSH_TRACE") != nullptr;
         if (ctx->trace_on) { CK(ctx->trace.ensure(4 * 4096)); CK(cudaMemset(ctx->trace.p, 0, sizeof(u64) * 4 * 4096)); }
         CK(ctx->ctl.ensure(1));
@@ -1096,6 +1108,11 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     {
         const double f = getenv("FORA_PUSH_DENSE") ? atof(getenv("FORA_PUSH_DENSE")) : -1.0;
         a.dense_min = f < 0 ? 0xffffffffu : (u32)std::max(1.0, f * (double)ctx->g.n);
+    }
+    // edge lists of dense slot-levels (FORA_PUSH_EL=0: dense slot-levels go through the tiles with RED)
+    a.el = nullptr; a.el_cap = 0; a.el_count = nullptr; a.el_bad = nullptr;
+    if (a.dense_min != 0xffffffffu && ctx->g.off32 && ctx->el_cap) {
+        a.el = ctx->el.p; a.el_cap = (u32)ctx->el_cap; a.el_count = ctx->el_ctl.p; a.el_bad = ctx->el_ctl.p + 2 * MAX_SLOTS;
     }
     // lockstep phase B (FORA_PUSH_LOCKSTEP = group size in units of n edges, e.g. 0.125; unset / 0: off)
     {

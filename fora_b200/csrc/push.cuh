@@ -20,6 +20,7 @@
 // memory system's random read-modify-write rate).
 #pragma once
 #include <cooperative_groups.h>
+#include <cstddef>
 
 #include "common.cuh"
 
@@ -48,7 +49,8 @@ constexpr int PUSH_UB = CFG_PUSH_UB;       // edges in flight per lane in phase 
 #define CFG_PUSH_WQ 256
 #endif
 constexpr int PUSH_WQ = CFG_PUSH_WQ;     // per-warp queue of crossing vertices
-constexpr int SCAN_K = 8;                // dense scan: vertices per thread and tile (tile = 8 * 512 vertices)
+constexpr int SCAN_K = 32;               // dense scan: vertices per thread and tile (tile = 32 * 512 vertices)
+constexpr u32 SCAN_HCAP = 4096;          // hits of a tile handled per batch (their lists alias the idle phase-B staging arrays)
 
 // frontier entry: [slot:8][min(out-degree, 2^24-1):24][vertex:32].  Whoever appends a vertex has just loaded its
 // out-degree for the threshold test, so carrying it saves phase A one random access per vertex.
@@ -108,6 +110,13 @@ struct PushArgs {
     // lockstep phase B: the edge line is worked through in groups of whole slots of at least this many edges, with a grid barrier
     // between groups, so that the grid never has more than one or two residue vectors live in the L2 (0: one sweep, no barriers)
     u64 lockstep_edges;
+    // edge lists of dense slot-levels: the scan that finds a slot's next frontier also gathers that frontier's column words into a
+    // sequential (target, index of the pushing entry) list, and the next level's scatters of the slot stream that list (push_el_adds)
+    // instead of going through phase B's staging / owner search.  el = null: off.
+    uint2* el;          // [2][slots][el_cap] by level parity
+    u32 el_cap;         // edges per slot and level; a level that does not fit falls back to the tiles
+    u32* el_count;      // [2][MAX_SLOTS] edges listed for the slot's frontier of a level of that parity
+    u32* el_bad;        // [2][MAX_SLOTS] that list overflowed
 };
 
 // dynamic shared memory of the push kernel (~70 KB, two CTAs per SM)
@@ -132,10 +141,11 @@ struct PushSmem {
     unsigned char dense[MAX_SLOTS];  // this level: the slot scatters with RED and is scanned afterwards
     unsigned char adone[MAX_SLOTS];  // this level: the slot's frontier was made by a scan, its phase A is done
     u32 ndense;
+    u32 nf_all;                      // this level: some slot has a frontier
+    unsigned char el_ok[MAX_SLOTS];  // this level: the slot's edges are in its edge list (no phase A / phase B entries for it)
     u32 sc_cnt[SCAN_K * PUSH_WARPS];
     u32 sc_wtot[PUSH_WARPS];
-    u32 sc_base;
-    u32 sc_list[SCAN_K * PUSH_THREADS]; // hit vertices of a scan tile, in vertex order
+    u32 sc_base, sc_ebase, sc_etot;
     u64 gslot[MAX_SLOTS + 1];           // lockstep phase B: where each slot starts on the level's edge line
 };
 
@@ -548,12 +558,22 @@ __device__ __forceinline__ void push_phase_b(const PushArgs& a, const CsrView<Of
 // ---- dense scan of slot s after a level in which it scattered with RED: the vertices at or above their threshold ARE the
 // frontier of level + 1 (phase A zeroed the previous frontier, so nothing else can be above), and their phase A happens here:
 // residue zeroed, credit logged, increment written.  CTA `rank` owns a contiguous range of the vector, handled in tiles of
-// SCAN_K * PUSH_THREADS vertices: pass 1 reads residue and out-degree of the tile (SCAN_K independent loads of each in flight per
+// SCAN_K * PUSH_THREADS vertices: pass 1 reads residue and out-degree of the tile (eight independent loads of each in flight per
 // thread) and notes the hits; a block scan of the (k, warp) counts and ONE global atomic place the tile's hits in vertex order; the
-// hit vertices are compacted into shared memory; pass 2 walks that list with all lanes busy.  The frontier comes out sorted by
-// vertex id in runs of a tile, so the next level's column reads walk the CSR forward.  Whole CTA, contains CTA barriers.
+// hits are compacted into shared memory SCAN_HCAP at a time (the lists alias phase B's staging arrays, idle now); pass 2 walks that
+// list with all lanes busy.  With an edge list (a.el) the same batch is then expanded: exclusive scan of the hits' out-degrees, one
+// global atomic for the batch's place in the slot's list, and every thread copies column words (target, pushing entry) -- the
+// next level's scatters of this slot are a sequential stream.  Whole CTA, contains CTA barriers.
 template <typename OffT>
-__device__ __forceinline__ void push_dense_scan(const PushArgs& a, PushSmem<OffT>& sm, int s, u32 rank, u32 count, u64* nxt, u32* nxt_count) {
+__device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView<OffT>& g, PushSmem<OffT>& sm, int s, u32 level, u32 rank,
+                                                u32 count, u64* nxt, u32* nxt_count) {
+    static_assert(sizeof(sm.wqueue) >= 2 * SCAN_HCAP * sizeof(u32), "hit list + edge offsets alias the warp queues");
+    static_assert(sizeof(sm.G) + sizeof(sm.inc) >= SCAN_HCAP * sizeof(u32) && offsetof(PushSmem<OffT>, inc) == offsetof(PushSmem<OffT>, G) + sizeof(sm.G),
+                  "adjacency starts alias G + inc");
+    u32* h_list = reinterpret_cast<u32*>(&sm.wqueue[0][0]);   // hit vertices of the batch, in vertex order
+    u32* h_eoff = h_list + SCAN_HCAP;                           // out-degrees, then their exclusive prefix
+    u32* h_ptr = reinterpret_cast<u32*>(&sm.G[0]);              // adjacency starts (32-bit offsets only), ~0: dangling
+    const bool gather = sizeof(OffT) == 4 && a.el != nullptr;
     const int lane = lane_id(), w = threadIdx.x >> 5;
     const u32 n = (u32)a.n;
     const u32 per = (n + count - 1) / count;
@@ -561,68 +581,77 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, PushSmem<OffT
     double* res = a.residue + (size_t)s * n;
     const double rm = sm.rmax[s];
     const u32 lb = sm.logbase[s] + sm.prevcnt[s]; // log position of the first entry of the slot's next frontier
+    const u32 par = (level + 1) & 1;
+    uint2* el = gather ? a.el + ((size_t)par * a.slots + s) * a.el_cap : nullptr;
+    const u32 idmask = a.colx ? ((1u << a.deg_shift) - 1u) : 0xffffffffu;
+    const int32_t* __restrict__ colp = a.colx ? a.colx : g.col;
     u32 dsum_t = 0, vcnt_t = 0;
     for (u32 tb = lo; tb < hi; tb += SCAN_K * PUSH_THREADS) {
         u32 mask = 0;
-        {
-            double r[SCAN_K];
-            int32_t d[SCAN_K];
+        for (int k0 = 0; k0 < SCAN_K; k0 += 8) {
+            double r[8];
+            int32_t d[8];
 #pragma unroll
-            for (int k = 0; k < SCAN_K; ++k) {
-                const u32 v = tb + k * PUSH_THREADS + threadIdx.x;
-                r[k] = v < hi ? __ldcg(&res[v]) : 0.0; // L2, never a stale L1 line: the REDs of other SMs just landed there
-                d[k] = v < hi ? __ldg(&a.deg[v]) : 1;  // unconditionally: one round trip instead of two
+            for (int kk = 0; kk < 8; ++kk) {
+                const u32 v = tb + (k0 + kk) * PUSH_THREADS + threadIdx.x;
+                r[kk] = v < hi ? __ldcg(&res[v]) : 0.0; // L2, never a stale L1 line: the REDs of other SMs just landed there
+                d[kk] = v < hi ? __ldg(&a.deg[v]) : 1;  // unconditionally: one round trip instead of two
             }
 #pragma unroll
-            for (int k = 0; k < SCAN_K; ++k) {
-                const bool hit = r[k] > 0.0 && (d[k] ? (r[k] >= rm * (double)d[k]) : true);
+            for (int kk = 0; kk < 8; ++kk) {
+                const bool hit = r[kk] > 0.0 && (d[kk] ? (r[kk] >= rm * (double)d[kk]) : true);
                 const u32 bal = __ballot_sync(FULL, hit);
-                if (hit) mask |= 1u << k;
-                if (lane == 0) sm.sc_cnt[k * PUSH_WARPS + w] = __popc(bal);
+                if (hit) mask |= 1u << (k0 + kk);
+                if (lane == 0) sm.sc_cnt[(k0 + kk) * PUSH_WARPS + w] = __popc(bal);
             }
         }
         __syncthreads();
-        // exclusive scan of the SCAN_K * 16 (k, warp) counts in vertex order: thread t owns count t
-        const bool own = threadIdx.x < SCAN_K * PUSH_WARPS;
-        const u32 c = own ? sm.sc_cnt[threadIdx.x] : 0u;
+        // exclusive scan of the 512 (k, warp) counts in vertex order: thread t owns count t
+        const u32 c = sm.sc_cnt[threadIdx.x];
         const u32 incl = warp_incl_scan(c);
-        if (lane == 31) sm.sc_wtot[w] = incl; // warps beyond the counts write 0
+        if (lane == 31) sm.sc_wtot[w] = incl;
         __syncthreads();
         const u32 wt = lane < PUSH_WARPS ? sm.sc_wtot[lane] : 0u;
         const u32 wi = warp_incl_scan(wt);
         const u32 total = __shfl_sync(FULL, wi, PUSH_WARPS - 1);
         const u32 before = w ? __shfl_sync(FULL, wi, w - 1) : 0u;
         if (threadIdx.x == 0) sm.sc_base = total ? atomicAdd(&nxt_count[s], total) : 0u;
-        if (own) sm.sc_cnt[threadIdx.x] = before + incl - c; // every thread rewrites only the count it read itself
+        sm.sc_cnt[threadIdx.x] = before + incl - c; // every thread rewrites only the count it read itself
         __syncthreads();
-        if (total) { // block-uniform
-#pragma unroll
-            for (int k = 0; k < SCAN_K; ++k) { // compact the hit vertices, in vertex order
+        const u32 base = sm.sc_base;
+        u64* seg = nxt + (size_t)s * n;
+        double* incs = a.inc + (size_t)s * n;
+        for (u32 hb = 0; hb < total; hb += SCAN_HCAP) { // block-uniform; one batch unless a tile is very dense
+            const u32 nb = min(SCAN_HCAP, total - hb);
+#pragma unroll 8
+            for (int k = 0; k < SCAN_K; ++k) { // compact the batch's hit vertices, in vertex order
                 const bool hit = (mask >> k) & 1u;
                 const u32 bal = __ballot_sync(FULL, hit);
-                if (hit) sm.sc_list[sm.sc_cnt[k * PUSH_WARPS + w] + __popc(bal & lanemask_lt())] = tb + k * PUSH_THREADS + threadIdx.x;
+                if (hit) {
+                    const u32 rk = sm.sc_cnt[k * PUSH_WARPS + w] + __popc(bal & lanemask_lt()) - hb; // wraps below the batch
+                    if (rk < nb) h_list[rk] = tb + k * PUSH_THREADS + threadIdx.x;
+                }
             }
             __syncthreads();
-            const u32 base = sm.sc_base;
-            u64* seg = nxt + (size_t)s * n;
-            double* incs = a.inc + (size_t)s * n;
-            for (u32 h0 = 0; h0 < total; h0 += 4 * PUSH_THREADS) {
-                u32 v[4], d[4];
+            for (u32 h0 = 0; h0 < nb; h0 += 4 * PUSH_THREADS) {
+                u32 v[4], d[4], pb[4];
                 double r[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const u32 h = h0 + q * PUSH_THREADS + threadIdx.x;
-                    v[q] = h < total ? sm.sc_list[h] : 0xffffffffu;
-                    r[q] = 0.0; d[q] = 0;
+                    v[q] = h < nb ? h_list[h] : 0xffffffffu;
+                    r[q] = 0.0; d[q] = 0; pb[q] = 0;
                     if (v[q] != 0xffffffffu) {
                         r[q] = __ldcg(&res[v[q]]);
                         d[q] = (u32)__ldg(&a.deg[v[q]]);
+                        if (gather) pb[q] = (u32)g.ptr[v[q]];
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     if (v[q] == 0xffffffffu) continue;
-                    const u32 j = base + h0 + q * PUSH_THREADS + threadIdx.x;
+                    const u32 h = h0 + q * PUSH_THREADS + threadIdx.x;
+                    const u32 j = base + hb + h;
                     res[v[q]] = 0.0;
                     seg[j] = make_entry(s, d[q], (int32_t)v[q]);
                     const u32 lp = lb + j;
@@ -635,17 +664,107 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, PushSmem<OffT
                         *rp = __ldcg(rp) + r[q] * a.alpha;
                     }
                     incs[j] = d[q] ? ((1.0 - a.alpha) * r[q]) / (double)d[q] : r[q] * (1.0 - a.alpha);
+                    if (gather) {
+                        h_eoff[h] = d[q] ? d[q] : 1u;          // a dangling vertex owns one pseudo-edge back to the source
+                        h_ptr[h] = d[q] ? pb[q] : 0xffffffffu;
+                    }
                     dsum_t += d[q];
                     ++vcnt_t;
                 }
             }
+            if (gather) {
+                __syncthreads();
+                // exclusive scan of the batch's out-degrees: eight consecutive hits per thread
+                u32 loc[8], tsum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const u32 h = threadIdx.x * 8 + q;
+                    loc[q] = tsum;
+                    tsum += h < nb ? h_eoff[h] : 0u;
+                }
+                const u32 ti = warp_incl_scan(tsum);
+                if (lane == 31) sm.sc_wtot[w] = ti;
+                __syncthreads();
+                const u32 wt2 = lane < PUSH_WARPS ? sm.sc_wtot[lane] : 0u;
+                const u32 wi2 = warp_incl_scan(wt2);
+                const u32 etot = __shfl_sync(FULL, wi2, PUSH_WARPS - 1);
+                const u32 tbase = (w ? __shfl_sync(FULL, wi2, w - 1) : 0u) + ti - tsum;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const u32 h = threadIdx.x * 8 + q;
+                    if (h < nb) h_eoff[h] = tbase + loc[q];
+                }
+                if (threadIdx.x == 0) {
+                    const u32 eb = atomicAdd(&a.el_count[par * MAX_SLOTS + s], etot);
+                    sm.sc_ebase = eb;
+                    sm.sc_etot = etot;
+                    if ((u64)eb + etot > a.el_cap) { a.el_bad[par * MAX_SLOTS + s] = 1; sm.sc_etot = 0; } // the level falls back to the tiles
+                }
+                __syncthreads();
+                const u32 ebase = sm.sc_ebase, T = sm.sc_etot;
+                for (u32 x0 = 0; x0 < T; x0 += 4 * PUSH_THREADS) {
+                    u32 hq[4], uq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const u32 x = x0 + q * PUSH_THREADS + threadIdx.x;
+                        hq[q] = 0xffffffffu; uq[q] = 0;
+                        if (x < T) {
+                            u32 l = 0, h = nb; // largest l with h_eoff[l] <= x
+                            while (h - l > 1) {
+                                const u32 mid = (l + h) >> 1;
+                                if (h_eoff[mid] <= x) l = mid;
+                                else h = mid;
+                            }
+                            hq[q] = l;
+                            const u32 p0 = h_ptr[l];
+                            uq[q] = p0 == 0xffffffffu ? (u32)sm.source[s] : ((u32)__ldcs(&colp[p0 + (x - h_eoff[l])]) & idmask);
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const u32 x = x0 + q * PUSH_THREADS + threadIdx.x;
+                        if (hq[q] != 0xffffffffu) el[ebase + x] = make_uint2(uq[q], base + hb + hq[q]);
+                    }
+                }
+            }
+            __syncthreads(); // the lists are rewritten by the next batch / tile
         }
-        __syncthreads(); // sc_cnt / sc_base / sc_list are rewritten by the next tile
+        __syncthreads(); // sc_cnt / sc_base
     }
     const u32 ds = warp_sum(dsum_t), vc = warp_sum(vcnt_t);
     if (lane == 0 && vc) {
         atomicAdd(&sm.cnt_edges[s], ds);
         atomicAdd(&sm.cnt_verts[s], vc);
+    }
+}
+
+// ---- the scatters of a slot whose edges are in its edge list: a sequential stream of (target, pushing entry) pairs, four of them and
+// their increments in flight per thread, fp64 RED (the scan that follows finds the next frontier).  Contiguous share per CTA.
+template <typename OffT>
+__device__ __forceinline__ void push_el_adds(const PushArgs& a, PushSmem<OffT>& sm, int s, u32 level, u32 rank, u32 count) {
+    const u32 par = level & 1;
+    const u32 E = min(*(volatile u32*)&a.el_count[par * MAX_SLOTS + s], a.el_cap);
+    const uint2* __restrict__ el = a.el + ((size_t)par * a.slots + s) * a.el_cap;
+    const double* incs = a.inc + (size_t)s * a.n;
+    double* res = a.residue + (size_t)s * a.n;
+    const u32 lo = (u32)(((u64)E * rank) / count), hi = (u32)(((u64)E * (rank + 1)) / count);
+    const u64 pol_keep = l2_policy_evict_last();
+    for (u32 x0 = lo + threadIdx.x; x0 < hi; x0 += 4 * PUSH_THREADS) {
+        uint2 e[4];
+        double inc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const u32 x = x0 + q * PUSH_THREADS;
+            e[q] = x < hi ? __ldcs(&el[x]) : make_uint2(0xffffffffu, 0u);
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) inc[q] = e[q].x != 0xffffffffu ? __ldcg(&incs[e[q].y]) : 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (e[q].x != 0xffffffffu) {
+                if (a.l2_hints) red_add_f64_hint(&res[e[q].x], inc[q], pol_keep);
+                else atomicAdd(&res[e[q].x], inc[q]);
+            }
     }
 }
 
@@ -673,17 +792,27 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
             const int l = threadIdx.x;
             const u32 c0 = l < a.slots ? *((volatile u32*)&ctl->fcount[level % 3][l]) : 0u;
             const u32 c1 = l + WARP < a.slots ? *((volatile u32*)&ctl->fcount[level % 3][l + WARP]) : 0u;
-            const u32 i0 = warp_incl_scan(c0);
-            const u32 i1 = warp_incl_scan(c1) + __shfl_sync(FULL, i0, 31);
-            if (l < a.slots) { sm.fbase[l] = i0 - c0; sm.logbase[l] += sm.prevcnt[l]; sm.prevcnt[l] = c0; }
-            if (l + WARP < a.slots) { sm.fbase[l + WARP] = i1 - c1; sm.logbase[l + WARP] += sm.prevcnt[l + WARP]; sm.prevcnt[l + WARP] = c1; }
-            if (l == 31) sm.fbase[a.slots] = i1;
-            // a slot that scattered with RED was scanned: its frontier is ready-made; large frontiers scatter with RED this time
+            // a slot that scattered with RED was scanned: its frontier is ready-made; large frontiers scatter with RED this time; a slot
+            // that was scanned AND is large again has its edges in its edge list and takes no part in phase A / phase B
             const bool d0 = DN && c0 >= a.dense_min && c0 > 0, d1 = DN && c1 >= a.dense_min && c1 > 0;
-            if (l < a.slots) { sm.adone[l] = sm.dense[l]; sm.dense[l] = d0; }
-            if (l + WARP < a.slots) { sm.adone[l + WARP] = sm.dense[l + WARP]; sm.dense[l + WARP] = d1; }
+            const bool a0 = l < a.slots && sm.dense[l], a1 = l + WARP < a.slots && sm.dense[l + WARP]; // dense at the previous level
+            bool e0 = false, e1 = false;
+            if (DN && a.el) {
+                const u32 par = level & 1;
+                if (a0 && d0) e0 = *((volatile u32*)&a.el_bad[par * MAX_SLOTS + l]) == 0;
+                if (a1 && d1) e1 = *((volatile u32*)&a.el_bad[par * MAX_SLOTS + l + WARP]) == 0;
+            }
+            const u32 f0 = e0 ? 0u : c0, f1 = e1 ? 0u : c1; // entries that go through phase A / phase B
+            const u32 i0 = warp_incl_scan(f0);
+            const u32 i1 = warp_incl_scan(f1) + __shfl_sync(FULL, i0, 31);
+            if (l < a.slots) { sm.fbase[l] = i0 - f0; sm.logbase[l] += sm.prevcnt[l]; sm.prevcnt[l] = c0; }
+            if (l + WARP < a.slots) { sm.fbase[l + WARP] = i1 - f1; sm.logbase[l + WARP] += sm.prevcnt[l + WARP]; sm.prevcnt[l + WARP] = c1; }
+            if (l == 31) sm.fbase[a.slots] = i1;
+            if (l < a.slots) { sm.adone[l] = a0; sm.dense[l] = d0; sm.el_ok[l] = e0; }
+            if (l + WARP < a.slots) { sm.adone[l + WARP] = a1; sm.dense[l + WARP] = d1; sm.el_ok[l + WARP] = e1; }
             const u32 nd = __popc(__ballot_sync(FULL, d0)) + __popc(__ballot_sync(FULL, d1));
-            if (l == 0) sm.ndense = nd;
+            const u32 anyc = __ballot_sync(FULL, c0 != 0 || c1 != 0);
+            if (l == 0) { sm.ndense = nd; sm.nf_all = anyc ? 1u : 0u; }
             if (blockIdx.x == 0) { // levels in which the slot pushed something
                 const int lvl = (int)(a.level_base + level + 1);
                 if (level < a.max_levels) {
@@ -693,8 +822,8 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
             }
         }
         __syncthreads();
-        const u32 nf = sm.fbase[a.slots];
-        if (nf == 0) break;
+        const u32 nf = sm.fbase[a.slots]; // (may be 0 while slots with an edge list still have work)
+        if (!sm.nf_all) break;
         if (level >= a.max_levels) { // never reached in practice (2^20 levels): report instead of dropping the frontier silently
             if (blockIdx.x == 0 && threadIdx.x == 0 && a.err) *a.err = 1;
             if (threadIdx.x < (u32)a.slots) sm.prevcnt[threadIdx.x] = 0; // the counts just read belong to a level that did not run: not logged
@@ -705,14 +834,20 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         u64* nxt = (level & 1) ? a.front0 : a.front1;
         u32* nxt_count = ctl->fcount[(level + 1) % 3];
         if (blockIdx.x == 0) {
-            if (threadIdx.x < (u32)a.slots) ctl->fcount[(level + 2) % 3][threadIdx.x] = 0;
+            if (threadIdx.x < (u32)a.slots) {
+                ctl->fcount[(level + 2) % 3][threadIdx.x] = 0;
+                if (DN && a.el) { // the lists of the next level's parity were consumed a level ago
+                    a.el_count[((level + 1) & 1) * MAX_SLOTS + threadIdx.x] = 0;
+                    a.el_bad[((level + 1) & 1) * MAX_SLOTS + threadIdx.x] = 0;
+                }
+            }
             if (threadIdx.x == 0) {
                 ctl->levels_run = level + 1;
                 if (a.trace && level < a.trace_cap) {
                     u64 t;
                     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
                     a.trace[4 * level] = t;
-                    a.trace[4 * level + 1] = nf;
+                    a.trace[4 * level + 1] = nf | ((u64)sm.ndense << 40);
                 }
             }
         }
@@ -725,10 +860,34 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         }
         push_phase_b<OffT, DN>(a, g, sm, cur, nf, level, blockIdx.x, gridDim.x, nxt, nxt_count);
         grid.sync();
-        if (DN && sm.ndense) { // the slots that scattered with RED: next frontier + its phase A from one pass over the residue vector
-            for (int s = 0; s < a.slots; ++s)
-                if (sm.dense[s]) push_dense_scan<OffT>(a, sm, s, blockIdx.x, gridDim.x, nxt, nxt_count);
-            grid.sync();
+        if (DN && sm.ndense) {
+            // the dense slots, one after the other with the whole grid (their vectors stay in the L2 from the adds to the scan): a slot
+            // with an edge list streams its scatters now; then one pass over the residue vector finds the next frontier, does its
+            // phase A and lists its edges
+            for (int s = 0; s < a.slots; ++s) {
+                if (!sm.dense[s]) continue;
+                // (development trace, CTA 0: own adds / wait / own scan + gather / wait, summed over the level's dense slots)
+                const bool tr = a.trace && blockIdx.x == 0 && level < 1024;
+                u64 t0 = 0, t1 = 0, t2 = 0, t3 = 0, t4 = 0;
+                if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+                if (sm.el_ok[s]) {
+                    push_el_adds<OffT>(a, sm, s, level, blockIdx.x, gridDim.x);
+                    if (tr) { __syncthreads(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1)); }
+                    grid.sync();
+                } else if (tr) t1 = t0;
+                if (tr) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t2));
+                push_dense_scan<OffT>(a, g, sm, s, level, blockIdx.x, gridDim.x, nxt, nxt_count);
+                if (tr) { __syncthreads(); asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t3)); }
+                if (a.el) grid.sync(); // (without edge lists the scans of different slots touch different vectors: one barrier at the end)
+                if (tr) {
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t4));
+                    if (threadIdx.x == 0) {
+                        u64* tx = a.trace + 4 * 1024 + 4 * level;
+                        tx[0] += t1 - t0; tx[1] += t2 - t1; tx[2] += t3 - t2; tx[3] += t4 - t3;
+                    }
+                }
+            }
+            if (!a.el) grid.sync();
         }
     }
     __syncthreads();

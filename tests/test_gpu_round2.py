@@ -231,6 +231,7 @@ print("RESULT" + json.dumps(out))
                 # lockstep kernel (push3.cuh): one group per level, one slot per group, hubs cut into small pieces, plain atomics
                 # first-generation kernel with dense slot-levels (RED + scan of the residue vector): always / from 1 % of the vertices
                 {"FORA_PUSH_V": "1", "FORA_PUSH_DENSE": "0"}, {"FORA_PUSH_V": "1", "FORA_PUSH_DENSE": "0.01", "FORA_PUSH_LOG": "0"},
+                {"FORA_PUSH_V": "1", "FORA_PUSH_DENSE": "0.005", "FORA_PUSH_EL": "0"},  # ... without the edge lists (tiles with RED)
                 # ... and with a lockstep phase B (grid barrier between groups of slots on the edge line)
                 {"FORA_PUSH_V": "1", "FORA_PUSH_LOCKSTEP": "0.05"}, {"FORA_PUSH_V": "1", "FORA_PUSH_LOCKSTEP": "0.5", "FORA_PUSH_DENSE": "0.02"},
                 # (push3.cuh) default thresholds; every slot-level dense (RED + scan); never dense with tiny groups; hubs cut into
