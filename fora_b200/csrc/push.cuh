@@ -576,8 +576,16 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
     const bool gather = sizeof(OffT) == 4 && a.el != nullptr;
     const int lane = lane_id(), w = threadIdx.x >> 5;
     const u32 n = (u32)a.n;
-    const u32 per = (n + count - 1) / count;
-    const u32 lo = min(n, rank * per), hi = min(n, lo + per);
+    // rows of 32 consecutive vertices are dealt to the CTAs round-robin: the relabelling puts the vertices that are hit at every level
+    // (and the hubs among them) at the front of the vector, a contiguous range per CTA left CTA 0 with most of the edges to gather
+    const u32 NR = (n + WARP - 1) / WARP;
+    const u32 rows_cta = rank < NR ? (NR - rank + count - 1) / count : 0u;
+    auto vertex_of = [&](u32 tile_row0, int k) -> u32 { // 0xffffffff: past the end
+        const u32 i = tile_row0 + (u32)k * PUSH_WARPS + (threadIdx.x >> 5);
+        if (i >= rows_cta) return 0xffffffffu;
+        const u32 v = (i * count + rank) * WARP + (threadIdx.x & 31);
+        return v < n ? v : 0xffffffffu;
+    };
     double* res = a.residue + (size_t)s * n;
     const double rm = sm.rmax[s];
     const u32 lb = sm.logbase[s] + sm.prevcnt[s]; // log position of the first entry of the slot's next frontier
@@ -586,16 +594,27 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
     const u32 idmask = a.colx ? ((1u << a.deg_shift) - 1u) : 0xffffffffu;
     const int32_t* __restrict__ colp = a.colx ? a.colx : g.col;
     u32 dsum_t = 0, vcnt_t = 0;
-    for (u32 tb = lo; tb < hi; tb += SCAN_K * PUSH_THREADS) {
+    // (development trace, CTA 0: where the scan's time goes -- stage boundaries summed per level behind the level records)
+    const bool tr = a.trace && rank == 0 && level < 1024;
+    u64 ts_prev = 0;
+    auto stamp = [&](int stage) {
+        if (!tr) return;
+        u64 t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (threadIdx.x == 0 && ts_prev) a.trace[4 * 2048 + 8 * level + stage] += t - ts_prev;
+        ts_prev = t;
+    };
+    stamp(7);
+    for (u32 tb = 0; tb < rows_cta; tb += SCAN_K * PUSH_WARPS) { // tile = 512 rows
         u32 mask = 0;
         for (int k0 = 0; k0 < SCAN_K; k0 += 8) {
             double r[8];
             int32_t d[8];
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
-                const u32 v = tb + (k0 + kk) * PUSH_THREADS + threadIdx.x;
-                r[kk] = v < hi ? __ldcg(&res[v]) : 0.0; // L2, never a stale L1 line: the REDs of other SMs just landed there
-                d[kk] = v < hi ? __ldg(&a.deg[v]) : 1;  // unconditionally: one round trip instead of two
+                const u32 v = vertex_of(tb, k0 + kk);
+                r[kk] = v != 0xffffffffu ? __ldcg(&res[v]) : 0.0; // L2, never a stale L1 line: the REDs of other SMs just landed there
+                d[kk] = v != 0xffffffffu ? __ldg(&a.deg[v]) : 1;  // unconditionally: one round trip instead of two
             }
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
@@ -606,6 +625,7 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
             }
         }
         __syncthreads();
+        stamp(0); // pass 1
         // exclusive scan of the 512 (k, warp) counts in vertex order: thread t owns count t
         const u32 c = sm.sc_cnt[threadIdx.x];
         const u32 incl = warp_incl_scan(c);
@@ -618,6 +638,7 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
         if (threadIdx.x == 0) sm.sc_base = total ? atomicAdd(&nxt_count[s], total) : 0u;
         sm.sc_cnt[threadIdx.x] = before + incl - c; // every thread rewrites only the count it read itself
         __syncthreads();
+        stamp(1); // count scan + place in the frontier
         const u32 base = sm.sc_base;
         u64* seg = nxt + (size_t)s * n;
         double* incs = a.inc + (size_t)s * n;
@@ -629,10 +650,11 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
                 const u32 bal = __ballot_sync(FULL, hit);
                 if (hit) {
                     const u32 rk = sm.sc_cnt[k * PUSH_WARPS + w] + __popc(bal & lanemask_lt()) - hb; // wraps below the batch
-                    if (rk < nb) h_list[rk] = tb + k * PUSH_THREADS + threadIdx.x;
+                    if (rk < nb) h_list[rk] = vertex_of(tb, k);
                 }
             }
             __syncthreads();
+            stamp(2); // compaction
             for (u32 h0 = 0; h0 < nb; h0 += 4 * PUSH_THREADS) {
                 u32 v[4], d[4], pb[4];
                 double r[4];
@@ -674,6 +696,7 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
             }
             if (gather) {
                 __syncthreads();
+                stamp(3); // pass 2
                 // exclusive scan of the batch's out-degrees: eight consecutive hits per thread
                 u32 loc[8], tsum = 0;
 #pragma unroll
@@ -701,6 +724,7 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
                     if ((u64)eb + etot > a.el_cap) { a.el_bad[par * MAX_SLOTS + s] = 1; sm.sc_etot = 0; } // the level falls back to the tiles
                 }
                 __syncthreads();
+                stamp(4); // degree scan + place in the edge list
                 const u32 ebase = sm.sc_ebase, T = sm.sc_etot;
                 for (u32 x0 = 0; x0 < T; x0 += 4 * PUSH_THREADS) {
                     u32 hq[4], uq[4];
@@ -728,6 +752,7 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
                 }
             }
             __syncthreads(); // the lists are rewritten by the next batch / tile
+            stamp(5); // expansion (or pass 2 without edge lists)
         }
         __syncthreads(); // sc_cnt / sc_base
     }

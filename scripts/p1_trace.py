@@ -22,10 +22,12 @@ E.L.fora_debug_push_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 lv = E.L.fora_debug_push_trace(E.h, out.ctypes.data, 4096)
 t = out[: 4 * lv].reshape(lv, 4).astype(np.int64)
 tx = out[4 * 1024: 4 * 1024 + 4 * lv].reshape(lv, 4).astype(np.int64)
+ts = out[4 * 2048: 4 * 2048 + 8 * lv].reshape(lv, 8).astype(np.int64)
 for i in range(lv - 1):
     dt = t[i + 1, 0] - t[i, 0]
     nf, nd = int(t[i, 1]) & ((1 << 40) - 1), int(t[i, 1]) >> 40
     line = "L%3d nf(A/B)=%9d E(A/B)=%10d dense %2d  level %9.1f us  phase A %7.1f us" % (i, nf, t[i, 2], nd, dt / 1e3, (t[i, 3] - t[i, 0]) / 1e3)
     if nd:
         line += "   per dense slot, CTA 0: adds %.1f wait %.1f scan+gather %.1f wait %.1f us" % tuple(tx[i, k] / 1e3 / nd for k in range(4))
+        line += " | scan stages: pass1 %.1f count %.1f compact %.1f pass2 %.1f degscan %.1f expand %.1f" % tuple(ts[i, k] / 1e3 / nd for k in range(6))
     print(line)
