@@ -175,7 +175,7 @@ struct fora_ctx {
     u32 p3_hub_deg = P3_HUB_DEG, p3_hub_piece = P3_HUB_PIECE;
     double p3_dense = 1.0 / 32;
     // first-generation kernel, dense slot-levels: edge lists (push.cuh push_dense_scan / push_el_adds)
-    DevBuf<uint2> el;
+    DevBuf<uint4> el;
     DevBuf<u32> el_ctl; // [2][MAX_SLOTS] counts, [2][MAX_SLOTS] overflow flags
     size_t el_cap = 0;
     // bulk walks (index build / Monte-Carlo / BiPPR) through the chunked walk kernel
@@ -891,8 +891,9 @@ static int ensure_slots(fora_ctx* ctx, double omega_max) {
         }
         ctx->el_cap = 0;
         if (getenv("FORA_PUSH_DENSE") && atof(getenv("FORA_PUSH_DENSE")) >= 0 && g.off32 && !(getenv("FORA_PUSH_EL") && atoi(getenv("FORA_PUSH_EL")) == 0)) {
-            // a slot-level's edges: at most the graph's; 2n covers every level of the graphs measured (LJ shape peaks at 0.85 n)
-            ctx->el_cap = (size_t)std::min<int64_t>(g.n_edges, 2 * (int64_t)n);
+            // a slot-level's edges: at most the graph's; n (16 bytes each) covers every level of the graphs measured (LJ shape peaks
+            // at 0.85 n); a level that does not fit takes the tiles
+            ctx->el_cap = (size_t)std::min<int64_t>(g.n_edges, (int64_t)(getenv("FORA_PUSH_EL_CAP") ? atof(getenv("FORA_PUSH_EL_CAP")) * (double)n : (double)n));
             CK(ctx->el.ensure(2 * (size_t)S * ctx->el_cap));
             CK(ctx->el_ctl.ensure(4 * MAX_SLOTS));
             CK(cudaMemsetAsync(ctx->el_ctl.p, 0, sizeof(u32) * 4 * MAX_SLOTS, ctx->stream));
@@ -1111,6 +1112,9 @@ static PushArgs make_push_args(fora_ctx* ctx) {
     }
     // edge lists of dense slot-levels (FORA_PUSH_EL=0: dense slot-levels go through the tiles with RED)
     a.el = nullptr; a.el_cap = 0; a.el_count = nullptr; a.el_bad = nullptr;
+    a.el_prefetch = getenv("FORA_EL_PF") ? (u32)atol(getenv("FORA_EL_PF")) : (1u << 20);
+    a.debug_el_skip = getenv("FORA_DEBUG_EL_SKIP") ? (u32)atol(getenv("FORA_DEBUG_EL_SKIP")) : 0u;
+    a.debug_el = getenv("FORA_DEBUG_EL") ? (u32)atoi(getenv("FORA_DEBUG_EL")) : 0u;
     if (a.dense_min != 0xffffffffu && ctx->g.off32 && ctx->el_cap) {
         a.el = ctx->el.p; a.el_cap = (u32)ctx->el_cap; a.el_count = ctx->el_ctl.p; a.el_bad = ctx->el_ctl.p + 2 * MAX_SLOTS;
     }

@@ -113,10 +113,13 @@ struct PushArgs {
     // edge lists of dense slot-levels: the scan that finds a slot's next frontier also gathers that frontier's column words into a
     // sequential (target, index of the pushing entry) list, and the next level's scatters of the slot stream that list (push_el_adds)
     // instead of going through phase B's staging / owner search.  el = null: off.
-    uint2* el;          // [2][slots][el_cap] by level parity
+    uint4* el;          // [2][slots][el_cap] by level parity: (target, 0, increment as two words) -- the add pass needs ONE load per edge
     u32 el_cap;         // edges per slot and level; a level that does not fit falls back to the tiles
     u32* el_count;      // [2][MAX_SLOTS] edges listed for the slot's frontier of a level of that parity
     u32* el_bad;        // [2][MAX_SLOTS] that list overflowed
+    u32 el_prefetch;    // vertices at the front of the slot's residue vector brought into the L2 before its adds start (hot after the relabelling)
+    u32 debug_el_skip;  // ablation: adds to vertices below this id are dropped
+    u32 debug_el;       // ablation (wrong answers, timing only): 1 adds go to hashed uniform targets, 2 no adds at all, 4 no hot accumulators
 };
 
 // dynamic shared memory of the push kernel (~70 KB, two CTAs per SM)
@@ -590,7 +593,7 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
     const double rm = sm.rmax[s];
     const u32 lb = sm.logbase[s] + sm.prevcnt[s]; // log position of the first entry of the slot's next frontier
     const u32 par = (level + 1) & 1;
-    uint2* el = gather ? a.el + ((size_t)par * a.slots + s) * a.el_cap : nullptr;
+    uint4* el = gather ? a.el + ((size_t)par * a.slots + s) * a.el_cap : nullptr;
     const u32 idmask = a.colx ? ((1u << a.deg_shift) - 1u) : 0xffffffffu;
     const int32_t* __restrict__ colp = a.colx ? a.colx : g.col;
     u32 dsum_t = 0, vcnt_t = 0;
@@ -727,27 +730,33 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
                 stamp(4); // degree scan + place in the edge list
                 const u32 ebase = sm.sc_ebase, T = sm.sc_etot;
                 for (u32 x0 = 0; x0 < T; x0 += 4 * PUSH_THREADS) {
-                    u32 hq[4], uq[4];
+                    u32 uq[4];
+                    double iq[4];
+                    bool okq[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const u32 x = x0 + q * PUSH_THREADS + threadIdx.x;
-                        hq[q] = 0xffffffffu; uq[q] = 0;
-                        if (x < T) {
+                        okq[q] = x < T;
+                        uq[q] = 0; iq[q] = 0.0;
+                        if (okq[q]) {
                             u32 l = 0, h = nb; // largest l with h_eoff[l] <= x
                             while (h - l > 1) {
                                 const u32 mid = (l + h) >> 1;
                                 if (h_eoff[mid] <= x) l = mid;
                                 else h = mid;
                             }
-                            hq[q] = l;
                             const u32 p0 = h_ptr[l];
+                            iq[q] = __ldcg(&incs[base + hb + l]); // written in pass 2 of this batch: an L2 hit, next to the column word
                             uq[q] = p0 == 0xffffffffu ? (u32)sm.source[s] : ((u32)__ldcs(&colp[p0 + (x - h_eoff[l])]) & idmask);
                         }
                     }
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const u32 x = x0 + q * PUSH_THREADS + threadIdx.x;
-                        if (hq[q] != 0xffffffffu) el[ebase + x] = make_uint2(uq[q], base + hb + hq[q]);
+                        if (okq[q]) {
+                            const u64 ib = (u64)__double_as_longlong(iq[q]);
+                            el[ebase + x] = make_uint4(uq[q], 0u, (u32)ib, (u32)(ib >> 32));
+                        }
                     }
                 }
             }
@@ -763,34 +772,66 @@ __device__ __forceinline__ void push_dense_scan(const PushArgs& a, const CsrView
     }
 }
 
-// ---- the scatters of a slot whose edges are in its edge list: a sequential stream of (target, pushing entry) pairs, four of them and
-// their increments in flight per thread, fp64 RED (the scan that follows finds the next frontier).  Contiguous share per CTA.
+// ---- the scatters of a slot whose edges are in its edge list: a sequential stream of (target, increment) pairs, eight of them in flight
+// per thread, fp64 RED (the scan that follows finds the next frontier).  Adds to the EL_HOT hottest vertices (lowest ids after the
+// relabelling: ~15 % of all adds, and the few 128-byte lines on which the L2 would serialise them) are collected in shared memory --
+// the accumulators alias the warp queues, idle now -- and leave as one RED per CTA and vertex.  Contiguous share per CTA.
+constexpr u32 EL_HOT = 4096;
 template <typename OffT>
 __device__ __forceinline__ void push_el_adds(const PushArgs& a, PushSmem<OffT>& sm, int s, u32 level, u32 rank, u32 count) {
+    static_assert(sizeof(sm.wqueue) >= EL_HOT * sizeof(double), "hot accumulators alias the warp queues");
+    double* acc = reinterpret_cast<double*>(&sm.wqueue[0][0]);
     const u32 par = level & 1;
     const u32 E = min(*(volatile u32*)&a.el_count[par * MAX_SLOTS + s], a.el_cap);
-    const uint2* __restrict__ el = a.el + ((size_t)par * a.slots + s) * a.el_cap;
-    const double* incs = a.inc + (size_t)s * a.n;
+    const uint4* __restrict__ el = a.el + ((size_t)par * a.slots + s) * a.el_cap;
     double* res = a.residue + (size_t)s * a.n;
     const u32 lo = (u32)(((u64)E * rank) / count), hi = (u32)(((u64)E * (rank + 1)) / count);
     const u64 pol_keep = l2_policy_evict_last();
-    for (u32 x0 = lo + threadIdx.x; x0 < hi; x0 += 4 * PUSH_THREADS) {
-        uint2 e[4];
-        double inc[4];
+    const u32 hot = min(EL_HOT, (u32)a.n);
+    // the hot front of the vector first: a hot line that has to be fetched from DRAM at its first touch stalls its L2 slice for the
+    // whole fill while hundreds of adds queue behind it (cold vector + graph targets: 159 us per 3.4 M adds, cold + uniform targets 46 us)
+    {
+        const u32 lines = min(a.el_prefetch, (u32)a.n) / 16u;
+        for (u32 i = rank * PUSH_THREADS + threadIdx.x; i < lines; i += count * PUSH_THREADS)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(res + (size_t)i * 16u));
+    }
+    for (u32 i = threadIdx.x; i < hot; i += PUSH_THREADS) acc[i] = 0.0;
+    __syncthreads();
+    double dummy = 0.0;
+    for (u32 x0 = lo + threadIdx.x; x0 < hi; x0 += 8 * PUSH_THREADS) {
+        uint4 e[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const u32 x = x0 + q * PUSH_THREADS;
-            e[q] = x < hi ? __ldcs(&el[x]) : make_uint2(0xffffffffu, 0u);
+        for (int q = 0; q < 8; ++q) {
+            u32 x = x0 + q * PUSH_THREADS;
+            if ((a.debug_el & 8u) && x < hi) x = lo + (u32)(((u64)(x - lo) * 7919u) % (u64)(hi - lo)); // ablation: entries in a scattered order
+            e[q] = x < hi ? __ldcs(&el[x]) : make_uint4(0xffffffffu, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) inc[q] = e[q].x != 0xffffffffu ? __ldcg(&incs[e[q].y]) : 0.0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (e[q].x != 0xffffffffu) {
-                if (a.l2_hints) red_add_f64_hint(&res[e[q].x], inc[q], pol_keep);
-                else atomicAdd(&res[e[q].x], inc[q]);
+        for (int q = 0; q < 8; ++q)
+            if (e[q].x != 0xffffffffu && !(a.debug_el & 2u) && e[q].x >= a.debug_el_skip) {
+                const double inc = __longlong_as_double((long long)(((u64)e[q].w << 32) | e[q].z));
+                if (a.debug_el & 1u) e[q].x = (u32)(((u64)((x0 + q * PUSH_THREADS) * 2654435761u) * (u32)a.n) >> 32);
+                if (a.debug_el & 64u) { // ablation: random targets with the generator's in-degree law, rank == id (scripts/ubench_hot.cu)
+                    const u32 h1 = (x0 + q * PUSH_THREADS) * 2654435761u + 12345u, h2 = (h1 ^ (h1 >> 15)) * 0x846ca68bu;
+                    const double uu = ((double)(h2 ^ (h2 >> 16)) + 0.5) * (1.0 / 4294967296.0);
+                    const double e1 = 1.0 - 1.0 / 1.3, aa = pow(50.0, e1), bb = pow((double)a.n + 50.0, e1);
+                    const double xx = pow(uu * (bb - aa) + aa, 1.0 / e1) - 50.0;
+                    e[q].x = xx < 0 ? 0u : min((u32)xx, (u32)a.n - 1u);
+                }
+                if (a.debug_el & 32u) e[q].x = (u32)(((u64)e[q].x * 1000003ull) % (u64)(u32)a.n); // ablation: same heat per vertex, hot vertices spread over the lines
+                if (e[q].x < hot && !(a.debug_el & 4u)) atomicAdd(&acc[e[q].x], inc);
+                else if (a.debug_el & 16u) dummy += atomicAdd(&res[e[q].x], inc); // ablation: ATOM with return instead of RED
+                else if (a.l2_hints) red_add_f64_hint(&res[e[q].x], inc, pol_keep);
+                else atomicAdd(&res[e[q].x], inc);
             }
     }
+    if (dummy == 123.456e300) acc[0] = dummy;
+    __syncthreads();
+    for (u32 i = threadIdx.x; i < hot; i += PUSH_THREADS) {
+        const double v = acc[i];
+        if (v != 0.0) atomicAdd(&res[i], v);
+    }
+    __syncthreads(); // the queues' memory is handed back
 }
 
 template <typename OffT, bool DN>
