@@ -1417,7 +1417,8 @@ static int push_wave(fora_ctx* ctx, int cnt, const int32_t* d_sources, double* f
 // its distribution (its walks are independent samples of the walk from v); estimates of queries of the SAME wave are correlated.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sw_max_kernel(int32_t n, const int32_t* __restrict__ srcs, const u64* __restrict__ woff,
-                                                     const u64* __restrict__ nsrc, const int32_t* __restrict__ slot_state, u32* __restrict__ cnt) {
+                                                     const u64* __restrict__ nsrc, const int32_t* __restrict__ slot_state, u32* __restrict__ cnt,
+                                                     u64* __restrict__ overflow) {
     const int slot = blockIdx.y;
     if (slot_state[slot] != 1) return;
     const u64 ns = nsrc[slot];
@@ -1425,6 +1426,7 @@ __global__ void __launch_bounds__(256) sw_max_kernel(int32_t n, const int32_t* _
     const u64* __restrict__ wo = woff + (size_t)slot * (n + 1);
     for (u64 i = blockIdx.x * (u64)blockDim.x + threadIdx.x; i < ns; i += (u64)gridDim.x * blockDim.x) {
         const u64 c = wo[i + 1] - wo[i];
+        if (c > 0xffffffffull) *overflow = 1; // (more than 2^32 walks from one vertex: the wave keeps its private walks)
         atomicMax(&cnt[sv[i]], (u32)min(c, (u64)0xffffffffu));
     }
 }
@@ -1452,7 +1454,7 @@ __global__ void __launch_bounds__(256) sw_compact_kernel(int32_t n, const u32* _
 }
 struct BulkPlan;
 static int launch_bulk(fora_ctx* ctx, const BulkPlan& bp, u64* hops_out, int parts, const std::function<int(int, u64, u64)>& after_part);
-static int build_shared_walks(fora_ctx* ctx, int no_zero_hop);
+static int build_shared_walks(fora_ctx* ctx, int no_zero_hop, bool* usable);
 
 static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_zero_hop, u32 round_tag, const u64* idx_used,
                      u32 part = 0, u32 nparts = 1, int groups = 1, const std::function<int(int, int)>& after_group = nullptr) {
@@ -1481,8 +1483,9 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.seed_lo = (u32)ctx->seed; wa.seed_hi = (u32)(ctx->seed >> 32);
     wa.with_idx = ctx->p.with_idx && ctx->has_index;
     const bool shared = ctx->shared_walks && !wa.with_idx && per_round == 0 && nparts == 1 && !idx_used;
+    bool shared_ok = false;
     if (shared) {
-        int brc = build_shared_walks(ctx, no_zero_hop);
+        int brc = build_shared_walks(ctx, no_zero_hop, &shared_ok);
         if (brc) return brc;
     }
     wa.srcs = ctx->srcs.p; wa.woff = ctx->woff.p; wa.incs = ctx->incs.p; wa.nsrc = m->nsrc; wa.nwalk = m->nwalk;
@@ -1490,7 +1493,7 @@ static int walk_wave(fora_ctx* ctx, double* ppr, int per_round, int opt, int no_
     wa.part = part; wa.nparts = nparts;
     wa.round_tag = round_tag; wa.ppr = ppr; wa.hops = m->hops; wa.idx_hits = m->idx_hits;
     wa.idx_off = ctx->idx_off.p; wa.idx_cnt = ctx->idx_cnt.p; wa.idx_dest = ctx->idx_dest.p; wa.idx_used = idx_used;
-    if (shared) { // every walk of the wave is a hit in the pool just built
+    if (shared && shared_ok) { // every walk of the wave is a hit in the pool just built
         wa.with_idx = 1;
         wa.all_idx = 1;
         wa.idx_off = ctx->sw_off.p; wa.idx_cnt = ctx->sw_cnt64.p; wa.idx_dest = ctx->sw_dest.p; wa.idx_used = nullptr;
@@ -1790,15 +1793,18 @@ static int launch_bulk_single(fora_ctx* ctx, int32_t source_internal, u64 count,
 }
 
 // the wave's walk pool: counts (max over slots), offsets, compacted plan, destinations (see sw_max_kernel)
-static int build_shared_walks(fora_ctx* ctx, int no_zero_hop) {
+static int build_shared_walks(fora_ctx* ctx, int no_zero_hop, bool* usable) {
+    *usable = false;
     const DeviceGraph& g = ctx->g;
     const size_t n = (size_t)g.n;
     const int S = ctx->slots;
     SlotMeta* m = ctx->meta.p;
     CK(ctx->sw_cnt.ensure(n)); CK(ctx->sw_cnt64.ensure(n)); CK(ctx->sw_off.ensure(n)); CK(ctx->sw_flag.ensure(n)); CK(ctx->sw_pos.ensure(n));
-    CK(ctx->sw_srcs.ensure(n)); CK(ctx->sw_woff.ensure(n + 3));
+    CK(ctx->sw_srcs.ensure(n)); CK(ctx->sw_woff.ensure(n + 4));
     CK(cudaMemsetAsync(ctx->sw_cnt.p, 0, sizeof(u32) * n, ctx->stream));
-    sw_max_kernel<<<dim3(ctx->num_sms * 4, S), 256, 0, ctx->stream>>>(g.n, ctx->srcs.p, ctx->woff.p, m->nsrc, m->state, ctx->sw_cnt.p);
+    u64* d_tot = ctx->sw_woff.p + n + 1; // three spare words behind the prefix: sources, walks, overflow flag
+    CK(cudaMemsetAsync(d_tot, 0, 3 * sizeof(u64), ctx->stream));
+    sw_max_kernel<<<dim3(ctx->num_sms * 4, S), 256, 0, ctx->stream>>>(g.n, ctx->srcs.p, ctx->woff.p, m->nsrc, m->state, ctx->sw_cnt.p, d_tot + 2);
     CKL();
     sw_flag_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(g.n, ctx->sw_cnt.p, ctx->sw_cnt64.p, ctx->sw_flag.p);
     CKL();
@@ -1809,14 +1815,15 @@ static int build_shared_walks(fora_ctx* ctx, int no_zero_hop) {
     CK(ctx->sw_tmp.ensure(tb));
     CK(cub::DeviceScan::ExclusiveSum(ctx->sw_tmp.p, tb, ctx->sw_cnt64.p, ctx->sw_off.p, (int)n, ctx->stream));
     CK(cub::DeviceScan::ExclusiveSum(ctx->sw_tmp.p, tb, ctx->sw_flag.p, ctx->sw_pos.p, (int)n, ctx->stream));
-    u64* d_tot = ctx->sw_woff.p + n + 1; // two spare words behind the prefix
     sw_compact_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(g.n, ctx->sw_cnt.p, ctx->sw_pos.p, ctx->sw_off.p, ctx->sw_srcs.p, ctx->sw_woff.p, d_tot);
     CKL();
-    u64 tot[2] = {0, 0};
+    u64 tot[3] = {0, 0, 0};
     CK(cudaMemcpyAsync(tot, d_tot, sizeof tot, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->sw_built_walks = tot[1];
     ctx->sw_built_hops = 0;
+    if (tot[2]) return FORA_OK; // a count beyond 32 bits: private walks for this wave
+    *usable = true;
     if (tot[1] == 0) return FORA_OK;
     CK(ctx->sw_dest.ensure((size_t)tot[1]));
     BulkPlan bp;
