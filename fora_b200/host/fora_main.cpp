@@ -42,6 +42,7 @@ struct Config {
     unsigned query_size = 1000, k = 500, hub_space_consum = 1;
     int gpus = 1, slots = 16;
     uint64_t seed = 0;
+    bool shared_walks = false; // --shared_walks: the queries of a wave draw their walks from one pool (fora_ctx_set_shared_walks)
     bool split = false; // --split: the GPUs of --gpus answer every query TOGETHER (whole-graph SSPPR on huge graphs)
     string get_graph_folder() const { return prefix + graph_alias + "/"; }
 };
@@ -147,6 +148,7 @@ static vector<Gpu> open_gpus(const GraphHost& g, bool need_in) {
         if (g_group) gp[d].ctx = fora_group_ctx(g_group, d);
         else if (fora_ctx_create(d, seed, &gp[d].ctx)) die(string("fora_b200: ") + fora_last_error(nullptr));
         CKF(gp[d].ctx, fora_ctx_set_slots(gp[d].ctx, g_group ? 1 : config.slots));
+        if (config.shared_walks) CKF(gp[d].ctx, fora_ctx_set_shared_walks(gp[d].ctx, 1));
         CKF(gp[d].ctx, fora_graph_build_from_edges(gp[d].ctx, g.n, g.m, g.src.data(), g.dst.data(), (int64_t)g.src.size(), need_in ? 1 : 0));
     }
     return gp;
@@ -285,6 +287,7 @@ static void display_time_usage(const Result& r, unsigned query_size) { // algo.h
     if (config.algo == "fora" || config.algo == "fwdpush") cout << (r.total_time > 0 ? r.push_time * 100.0 / r.total_time : 0) << "% for forward push cost" << endl;
     if (config.algo == "bippr") cout << (r.total_time > 0 ? r.push_time * 100.0 / r.total_time : 0) << "% for backward push cost" << endl;
     if (config.algo == "fora") cout << "-----------------------------" << endl;
+    if (config.shared_walks && !config.with_rw_idx) cout << "Average shared rand-walk pool hit ratio: " << (r.num_randwalk > 0 ? r.num_idx * 100.0 / r.num_randwalk : 0) << "%" << endl;
     if (config.with_rw_idx) cout << "Average rand-walk idx hit ratio: " << (r.num_randwalk > 0 ? r.num_idx * 100.0 / r.num_randwalk : 0) << "%" << endl;
     if (config.action == "topk" && r.real_topk_source_count > 0) {
         cout << "Average top-K Precision: " << r.precision / r.real_topk_source_count << endl;
@@ -593,7 +596,7 @@ int main(int argc, char* argv[]) {
                     "fora build [options]\nfora generate-ss-query [options]\nfora gen-exact-topk [options]\nfora\n\nalgo: \n  bippr\n  montecarlo\n  fora\n  fwdpush\n"
                     "options: \n  --prefix <prefix>\n  --epsilon <epsilon>\n  --dataset <dataset>\n  --query_size <queries count>\n  --k <top k>\n  --with_idx\n"
                     "  --exact_ppr_path <eaact-topk-pprs-path>\n  --rw_ratio <rand-walk cost ratio>\n  --result_dir <directory to place results>  --rmax_scale <scale of rmax>\n"
-                    "  --opt\n  --balanced\n  --gpus <number of GPUs>\n  --split (all GPUs on one query at a time)\n  --seed <rng seed>\n  --slots <concurrent queries per GPU>\n"
+                    "  --opt\n  --balanced\n  --gpus <number of GPUs>\n  --split (all GPUs on one query at a time)\n  --shared_walks (the queries of a wave share one pool of random walks)\n  --seed <rng seed>\n  --slots <concurrent queries per GPU>\n"
                  << endl;
             exit(0);
         }
@@ -622,6 +625,7 @@ int main(int argc, char* argv[]) {
         else if (arg == "--balanced") config.balanced = true;
         else if (arg == "--gpus") config.gpus = max(1, atoi(val(i + 1)));
         else if (arg == "--split") config.split = true;
+        else if (arg == "--shared_walks") config.shared_walks = true;
         else if (arg == "--seed") config.seed = strtoull(val(i + 1), nullptr, 10);
         else if (arg == "--slots") config.slots = max(1, atoi(val(i + 1)));
         else if (arg.substr(0, 2) == "--") {

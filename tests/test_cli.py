@@ -95,6 +95,11 @@ def test_cli_end_to_end(dataset):
     # multi-"GPU" sharding path with a single device is exercised through --gpus 1 --slots 3
     p = run(["query", "--algo", "fora", "--opt", "--query_size", "10", "--slots", "3", "--result_dir", d] + pre)
     assert "Average query time (s):" in p.stdout
+    # opt-in walk pool: every walk of every query is served by the pool of its wave, reported like index hits
+    p = run(["query", "--algo", "fora", "--opt", "--balanced", "--shared_walks", "--query_size", "10", "--slots", "4", "--result_dir", d] + pre)
+    assert "Average query time (s):" in p.stdout
+    hit = float([l for l in p.stdout.splitlines() if "pool hit ratio" in l][0].split(":")[1].strip("% "))
+    assert hit > 99
     if have_reference():
         # the (shim-built) reference reads the index and exact-top-k archives our CLI wrote
         R = Reference(g, epsilon=0.5, opt=1, with_idx=1)

@@ -19,7 +19,8 @@ EPS = 0.5
 TOPK_TOL = 0.01  # north_star: "top-k precision must match the reference's within 0.01"
 
 
-def test_livejournal_shape_accuracy_vs_exact_ppr():
+@pytest.mark.parametrize("shared", [0, 1])  # 1: the opt-in per-wave walk pool (fora_ctx_set_shared_walks) at the same scale
+def test_livejournal_shape_accuracy_vs_exact_ppr(shared):
     n, m = 4847571, 68993773
     src, dst = fb.synth_edges(n, m, 42)
     op, oc, _, _ = fb.csr_from_edges(n, src, dst, with_in=False)
@@ -28,6 +29,7 @@ def test_livejournal_shape_accuracy_vs_exact_ppr():
     E = fb.Engine(0, seed=2026, slots=12)
     E.upload_graph(n, m, op, oc)
     E.configure("fora", EPS, opt=1, balanced=1)  # the bench configuration: built-in --balanced calibration
+    E.set_shared_walks(bool(shared))
     rng = np.random.default_rng(43)              # the bench's query list (seed 43), first ids + structural extremes
     srcs = np.r_[rng.integers(0, n, 1000)[:9], [int(np.argmax(deg)), int(np.flatnonzero(deg == 1)[3]), int(np.flatnonzero(deg == 0)[5])]].astype(np.int32)
     ppr, stats, _ = E.query_batch("fora", srcs)
