@@ -889,6 +889,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         }
         __syncthreads();
         const u32 nf = sm.fbase[a.slots]; // (may be 0 while slots with an edge list still have work)
+        const u32 ndense = sm.ndense;     // (read now: warp 0 writes the next level's value while slower warps are still behind the last barrier)
         if (!sm.nf_all) break;
         if (level >= a.max_levels) { // never reached in practice (2^20 levels): report instead of dropping the frontier silently
             if (blockIdx.x == 0 && threadIdx.x == 0 && a.err) *a.err = 1;
@@ -926,7 +927,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
         }
         push_phase_b<OffT, DN>(a, g, sm, cur, nf, level, blockIdx.x, gridDim.x, nxt, nxt_count);
         grid.sync();
-        if (DN && sm.ndense) {
+        if (DN && ndense) {
             // the dense slots, one after the other with the whole grid (their vectors stay in the L2 from the adds to the scan): a slot
             // with an edge list streams its scatters now; then one pass over the residue vector finds the next frontier, does its
             // phase A and lists its edges
@@ -954,6 +955,7 @@ __global__ void __launch_bounds__(PUSH_THREADS, 2) push_kernel(PushArgs a, CsrVi
                 }
             }
             if (!a.el) grid.sync();
+            __syncthreads(); // nobody is still reading this level's flags when warp 0 writes the next level's
         }
     }
     __syncthreads();
