@@ -1825,7 +1825,8 @@ static int build_shared_walks(fora_ctx* ctx, int no_zero_hop, bool* usable) {
     if (tot[2]) return FORA_OK; // a count beyond 32 bits: private walks for this wave
     *usable = true;
     if (tot[1] == 0) return FORA_OK;
-    CK(ctx->sw_dest.ensure((size_t)tot[1]));
+    if (ctx->sw_dest.cap < (size_t)tot[1]) CK(ctx->sw_dest.ensure((size_t)tot[1] + (size_t)tot[1] / 2)); // headroom: pools differ from wave to wave, a
+                                                                                                        // reallocation is a device synchronisation
     BulkPlan bp;
     bp.d_srcs = ctx->sw_srcs.p; bp.d_woff = ctx->sw_woff.p; bp.nsrc = tot[0]; bp.nwalk = tot[1]; bp.out_dest = ctx->sw_dest.p;
     // one stream per wave: ctx seed x global index of the wave's first query (reproducible; a different cut of the query list into

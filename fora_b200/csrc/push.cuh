@@ -1061,24 +1061,26 @@ __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n,
     const double rm = next_rmax ? next_rmax[slot] : 0.0;
     double s = 0.0;
     u32 c = 0, ns = 0;
-    auto take = [&](double r, int v) { // same per-thread order as a plain strided loop: rsum stays bit-identical
+    const bool seeding = rm > 0.0;
+    auto take = [&](double r, int32_t d) { // same per-thread order as a plain strided loop: rsum stays bit-identical
         s += r;
         c += r > 0.0;
-        if (rm > 0.0 && r > 0.0) {
-            const int32_t d = deg[v];
-            ns += d ? (r >= rm * (double)d) : 1u;
-        }
+        if (seeding && r > 0.0) ns += d ? (r >= rm * (double)d) : 1u;
     };
     int v = lo + threadIdx.x;
     for (; v + 3 * RED_THREADS < hi; v += 4 * RED_THREADS) { // four independent loads in flight per thread
         const double r0 = res[v], r1 = res[v + RED_THREADS], r2 = res[v + 2 * RED_THREADS],
                      r3 = res[v + 3 * RED_THREADS];
-        take(r0, v);
-        take(r1, v + RED_THREADS);
-        take(r2, v + 2 * RED_THREADS);
-        take(r3, v + 3 * RED_THREADS);
+        // the out-degrees next to them, unconditionally when seeds are wanted (a load behind `r > 0` made every element two
+        // dependent round trips; the degree vector is shared by all slots and stays in the L2)
+        int32_t d0 = 0, d1 = 0, d2 = 0, d3 = 0;
+        if (seeding) { d0 = deg[v]; d1 = deg[v + RED_THREADS]; d2 = deg[v + 2 * RED_THREADS]; d3 = deg[v + 3 * RED_THREADS]; }
+        take(r0, d0);
+        take(r1, d1);
+        take(r2, d2);
+        take(r3, d3);
     }
-    for (; v < hi; v += RED_THREADS) take(res[v], v);
+    for (; v < hi; v += RED_THREADS) take(res[v], seeding ? deg[v] : 0);
     s_sum[threadIdx.x] = s;
     s_nnz[threadIdx.x] = c;
     s_seed[threadIdx.x] = ns;
@@ -1103,13 +1105,19 @@ __global__ void __launch_bounds__(RED_THREADS) residue_partial_kernel(int32_t n,
     }
     __syncthreads();
     u64* out = seeds + (size_t)slot * n + s_base + s_seed[threadIdx.x];
-    for (int v = lo + threadIdx.x; v < hi; v += RED_THREADS) {
-        const double r = res[v];
-        if (r > 0.0) {
-            const int32_t d = deg[v];
-            if (d ? (r >= rm * (double)d) : true) *out++ = make_entry(slot, (u32)d, v);
-        }
+    int v2 = lo + threadIdx.x;
+    auto emit = [&](double r, int32_t d, int vv) {
+        if (r > 0.0 && (d ? (r >= rm * (double)d) : true)) *out++ = make_entry(slot, (u32)d, vv);
+    };
+    for (; v2 + 3 * RED_THREADS < hi; v2 += 4 * RED_THREADS) { // same order as the count above, four elements in flight
+        const double r0 = res[v2], r1 = res[v2 + RED_THREADS], r2 = res[v2 + 2 * RED_THREADS], r3 = res[v2 + 3 * RED_THREADS];
+        const int32_t d0 = deg[v2], d1 = deg[v2 + RED_THREADS], d2 = deg[v2 + 2 * RED_THREADS], d3 = deg[v2 + 3 * RED_THREADS];
+        emit(r0, d0, v2);
+        emit(r1, d1, v2 + RED_THREADS);
+        emit(r2, d2, v2 + 2 * RED_THREADS);
+        emit(r3, d3, v2 + 3 * RED_THREADS);
     }
+    for (; v2 < hi; v2 += RED_THREADS) emit(res[v2], deg[v2], v2);
 }
 __global__ void residue_final_kernel(int nblocks, const double* __restrict__ part_sum, const u32* __restrict__ part_nnz,
                                      double* __restrict__ rsum, u64* __restrict__ nnz) {

@@ -99,6 +99,11 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(PlanArgs a) {
     u64 n_v[PLAN_VPT];
 #pragma unroll
     for (int k = 0; k < PLAN_VPT; ++k) r[k] = (live && v0 + k < a.n) ? a.residue[g0 + v0 + k] : 0.0;
+    // fill pass with the alpha*r credit: the PPR words are fetched together with the residues, not behind the block scan's two barriers
+    const bool credit_fill = FILL && (a.opt || a.per_round == 2) && !a.no_credit;
+    double pold[PLAN_VPT];
+#pragma unroll
+    for (int k = 0; k < PLAN_VPT; ++k) pold[k] = (credit_fill && live && v0 + k < a.n) ? a.ppr[g0 + v0 + k] : 0.0;
     u32 flags = 0;
     u64 walks = 0;
 #pragma unroll
@@ -146,7 +151,7 @@ __global__ void __launch_bounds__(PLAN_THREADS) plan_kernel(PlanArgs a) {
             a.srcs[g0 + pos] = v0 + k;
             a.woff[(size_t)slot * (a.n + 1) + pos] = wo;
             a.incs[g0 + pos] = inc[k];
-            if (credit) a.ppr[g0 + v0 + k] += __dmul_rn(r[k], a.alpha); // query.h:363 / 562
+            if (credit) a.ppr[g0 + v0 + k] = pold[k] + __dmul_rn(r[k], a.alpha); // query.h:363 / 562
             ++pos;
             wo += n_v[k];
         }
